@@ -1,0 +1,91 @@
+"""ctypes binding of ``libgeom_b200.so`` (C ABI declared in ``include/geom_b200.h``).
+
+There is deliberately no fallback: if the CUDA library has not been built (``python -c "import
+__graft_entry__ as g; g.build()"`` or ``make -C geometrics_b200/csrc``) every operator raises
+:class:`GeomLibraryError`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgeom_b200.so")
+
+GEOM_ABI_VERSION = 1
+GEOM_FLAG_NONE = 0
+GEOM_FLAG_EXACT_TAIL = 1
+GEOM_FLAG_ONEWAY = 2
+
+# every symbol include/geom_b200.h declares: name -> (restype, argtypes)
+_vp, _i, _u, _sz = C.c_void_p, C.c_int, C.c_uint, C.c_size_t
+SYMBOLS = {
+    "geom_abi_version": (_i, []),
+    "geom_status_string": (C.c_char_p, [_i]),
+    "geom_device_info": (_i, [C.POINTER(_i)] * 3),
+    "geom_chamfer_workspace_bytes": (_sz, [_i, _i, _i]),
+    "geom_chamfer_fwd": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _u, _vp]),
+    "geom_tri_fwd": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _u, _vp]),
+}
+
+
+class GeomLibraryError(RuntimeError):
+    pass
+
+
+_lock = threading.Lock()
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the CUDA library; raise loudly when it is missing or stale."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise GeomLibraryError(
+                f"{LIB_PATH} not found: the sm_100a CUDA library is not built and geometrics_b200 has "
+                "no CPU fallback. Run `make -C geometrics_b200/csrc` (or __graft_entry__.build())."
+            )
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            try:
+                fn = getattr(L, name)
+            except AttributeError as exc:  # pragma: no cover - stale build
+                raise GeomLibraryError(f"{LIB_PATH} does not export {name}; rebuild it") from exc
+            fn.restype = res
+            fn.argtypes = args
+        if L.geom_abi_version() != GEOM_ABI_VERSION:
+            raise GeomLibraryError(f"{LIB_PATH} has ABI {L.geom_abi_version()}, expected {GEOM_ABI_VERSION}; rebuild it")
+        _lib = L
+    return _lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = lib().geom_status_string(status).decode()
+        raise RuntimeError(f"{what} failed: {msg} (status {status})")
+
+
+def require_cuda_f32(name: str, t, last=None):
+    """Argument validation the reference never did: fp32, CUDA, optional last dim."""
+    import torch
+
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (geometrics_b200 has no CPU path); got device {t.device}")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    if last is not None and (t.dim() != 3 or t.shape[-1] != last):
+        raise ValueError(f"{name} must have shape (B, N, {last}), got {tuple(t.shape)}")
+
+
+def current_stream_ptr(device) -> int:
+    import torch
+
+    return torch.cuda.current_stream(device).cuda_stream

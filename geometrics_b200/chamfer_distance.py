@@ -1,0 +1,65 @@
+"""Drop-in for the reference's ``chamfer_distance.ChamferDistance``.
+
+Same call surface as ``chamfer_distance/chamfer_distance.py:9-38`` of the reference:
+``ChamferDistance()(xyz1, xyz2) -> (idx1, idx2)`` with ``idx1`` int32 (B,n) = nearest xyz2 point of
+every xyz1 point and ``idx2`` int32 (B,m) the converse, both on the inputs' CUDA device.  The search
+itself is ``geom_chamfer_fwd`` in ``libgeom_b200.so`` (sm_100a); outputs are allocated on the device
+(the reference built them on the CPU and copied, :16-26) and the kernels run on torch's current
+stream (the reference used the legacy default stream).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+
+def chamfer_forward(xyz1: torch.Tensor, xyz2: torch.Tensor, *, exact_tail: bool = False,
+                    oneway: bool = False, want_dist: bool = True):
+    """-> (dist1, idx1, dist2, idx2); squared distances are fp32 (B,n)/(B,m) or None."""
+    _lib.require_cuda_f32("xyz1", xyz1, 3)
+    _lib.require_cuda_f32("xyz2", xyz2, 3)
+    if xyz1.shape[0] != xyz2.shape[0]:
+        raise ValueError(f"batch mismatch: xyz1 {tuple(xyz1.shape)} vs xyz2 {tuple(xyz2.shape)}")
+    if xyz1.device != xyz2.device:
+        raise RuntimeError(f"xyz1 on {xyz1.device} but xyz2 on {xyz2.device}")
+    L = _lib.lib()
+    xyz1 = xyz1.detach().contiguous()  # the reference also calls .contiguous() (:14-15)
+    xyz2 = xyz2.detach().contiguous()
+    b, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    dev = xyz1.device
+    with torch.cuda.device(dev):
+        idx1 = torch.empty((b, n), dtype=torch.int32, device=dev)
+        idx2 = torch.empty((b, m), dtype=torch.int32, device=dev)
+        dist1 = torch.empty((b, n), dtype=torch.float32, device=dev) if want_dist else None
+        dist2 = torch.empty((b, m), dtype=torch.float32, device=dev) if want_dist else None
+        ws_bytes = L.geom_chamfer_workspace_bytes(b, n, m)
+        ws = torch.empty((max(ws_bytes, 8) + 7) // 8, dtype=torch.int64, device=dev)
+        flags = (_lib.GEOM_FLAG_EXACT_TAIL if exact_tail else 0) | (_lib.GEOM_FLAG_ONEWAY if oneway else 0)
+        st = L.geom_chamfer_fwd(
+            b, n, xyz1.data_ptr(), m, xyz2.data_ptr(),
+            dist1.data_ptr() if want_dist else None, idx1.data_ptr(),
+            dist2.data_ptr() if want_dist else None, idx2.data_ptr(),
+            ws.data_ptr(), ws.numel() * 8, flags, _lib.current_stream_ptr(dev))
+        _lib.check(st, "geom_chamfer_fwd")
+    return dist1, idx1, dist2, idx2
+
+
+class ChamferDistanceFunction(torch.autograd.Function):
+    """Forward-only, like the reference (:9-31): integer outputs carry no gradient."""
+
+    @staticmethod
+    def forward(ctx, xyz1, xyz2):
+        _, idx1, _, idx2 = chamfer_forward(xyz1, xyz2, want_dist=False)
+        ctx.mark_non_differentiable(idx1, idx2)
+        return idx1, idx2
+
+    @staticmethod
+    def backward(ctx, *grads):  # pragma: no cover - outputs are non-differentiable
+        return None, None
+
+
+class ChamferDistance(torch.nn.Module):
+    def forward(self, xyz1, xyz2):
+        return ChamferDistanceFunction.apply(xyz1, xyz2)

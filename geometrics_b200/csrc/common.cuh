@@ -1,0 +1,81 @@
+// common.cuh -- shared device helpers for libgeom_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/geom_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libgeom_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace geom {
+
+typedef unsigned long long u64;
+
+// ---- packed fp32x2 arithmetic (Blackwell FADD2 / FMUL2 / FFMA2), IEEE round-to-nearest per half ----
+__device__ __forceinline__ u64 pack2(float lo, float hi)
+{
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(u64 v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b)
+{
+    u64 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b)
+{
+    u64 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c)
+{
+    u64 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+// 3-input minimum (FMNMX3).  NaN operands are ignored unless all are NaN.
+__device__ __forceinline__ float min3(float a, float b, float c)
+{
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
+// Squared distance with the reference's rounding sequence (chamfer_distance.cu:35-38 as compiled):
+// d = fma(dz,dz, fma(dx,dx, rn(dy*dy))), d* = candidate - query.
+__device__ __forceinline__ float sqdist_ref(float qx, float qy, float qz, float cx, float cy, float cz)
+{
+    const float dx = __fsub_rn(cx, qx);
+    const float dy = __fsub_rn(cy, qy);
+    const float dz = __fsub_rn(cz, qz);
+    return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+}
+
+// (distance bits << 32) | tag.  Distances are >= +0, so their bit patterns order like the values and
+// an unsigned 64-bit min picks the smallest distance, then the smallest tag.
+__device__ __forceinline__ u64 make_key(float d, unsigned tag)
+{
+    return ((u64)__float_as_uint(d) << 32) | (u64)tag;
+}
+
+// Filtered atomic min: the plain read may be stale, but keys only ever decrease, so a stale value
+// can only cause a redundant atomic, never a missed update.
+__device__ __forceinline__ void key_min(u64 *addr, u64 key)
+{
+    const u64 cur = *(volatile u64 *)addr;
+    if (key < cur) atomicMin(addr, key);
+}
+
+inline int status_from_cuda(cudaError_t e) { return e == cudaSuccess ? GEOM_OK : (int)e; }
+
+}  // namespace geom

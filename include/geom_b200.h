@@ -1,0 +1,94 @@
+/*
+ * geom_b200.h -- C ABI of libgeom_b200.so: the B200 (sm_100a) implementation of the GEOMetrics
+ * geometric hot path.  Plain pointers and sizes only; no torch / ATen types.
+ *
+ * Every entry point names the reference interface it replaces (paths relative to the reference
+ * repository root).  Conventions shared by all entry points:
+ *   - all pointers are DEVICE pointers on the current CUDA device unless stated otherwise;
+ *   - tensors are dense row-major fp32 / int32, exactly the layouts the reference passes
+ *     (points (B,N,3); per-face vertices (B,F,3); indices (B,N));
+ *   - the caller allocates every output and every workspace; nothing is retained across calls,
+ *     there is no global state, calls are thread-safe;
+ *   - work is enqueued on `stream` (a cudaStream_t; 0 = legacy default stream, which is what the
+ *     reference launchers use, chamfer_distance.cu:67-68 / tri_distance.cu:223) and the call
+ *     returns without synchronising;
+ *   - return value: 0 = success, <0 = GEOM_ERR_* (argument errors), >0 = a cudaError_t value.
+ *     (The reference launchers are declared `int` in the .cpp but defined `void` in the .cu and
+ *     only printf CUDA errors: chamfer_distance.cpp:4 vs chamfer_distance.cu:57,70-72.)
+ */
+#ifndef GEOM_B200_H
+#define GEOM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *geom_stream_t; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define GEOM_API __attribute__((visibility("default")))
+#else
+#define GEOM_API
+#endif
+
+#define GEOM_ABI_VERSION 1
+
+#define GEOM_OK 0
+#define GEOM_ERR_INVALID_ARG (-1) /* null pointer, negative size, unsupported size */
+#define GEOM_ERR_WORKSPACE (-2)   /* workspace null or smaller than *_workspace_bytes() */
+#define GEOM_ERR_UNSUPPORTED_DEVICE (-3)
+
+/* flags */
+#define GEOM_FLAG_NONE 0u
+/* Scan every candidate.  Default (flag clear) is bit-compatible with the reference kernels, which
+ * skip the last (m mod 512) mod 4 candidates of the final 512-tile (chamfer_distance.cu:31-33,
+ * tri_distance.cu:129,134) and, for Chamfer, zero every output when that final tile holds 1-3
+ * candidates (chamfer_distance.cu:29-30,47). */
+#define GEOM_FLAG_EXACT_TAIL 1u
+/* Chamfer only: use the simple one-direction-at-a-time kernel instead of the fused two-way one. */
+#define GEOM_FLAG_ONEWAY 2u
+
+GEOM_API int geom_abi_version(void);
+/* Static string for a status returned by any geom_* call. */
+GEOM_API const char *geom_status_string(int status);
+/* SM count and compute capability of the current device (the library is built for sm_100a only). */
+GEOM_API int geom_device_info(int *sm_count, int *cc_major, int *cc_minor);
+
+/* ---------------------------------------------------------------------------------------------
+ * Chamfer nearest-neighbour search.
+ * Replaces: ChamferDistanceKernelLauncher(b,n,xyz,m,xyz2,result,result_i,result2,result2_i)
+ *           chamfer_distance/chamfer_distance.cu:57-73 (bound from chamfer_distance.cpp:15-27).
+ * For every point j of xyz1 (B,n,3): idx1[j] = argmin_k ||xyz2[k]-xyz1[j]||^2, dist1[j] = that
+ * squared distance; and the same with roles swapped into (dist2, idx2) of shape (B,m).
+ * Ties: lowest candidate index (chamfer_distance.cu:39,47).  Arithmetic per pair:
+ * fma(dz,dz, fma(dx,dx, dy*dy)) with d* = candidate - query, as nvcc compiles :35-38.
+ * dist1 / dist2 may be NULL (the Python caller discards them, chamfer_distance.py:31).
+ * Inputs must be finite.
+ * ------------------------------------------------------------------------------------------- */
+GEOM_API size_t geom_chamfer_workspace_bytes(int b, int n, int m);
+GEOM_API int geom_chamfer_fwd(int b, int n, const float *xyz1, int m, const float *xyz2,
+                     float *dist1, int *idx1, float *dist2, int *idx2,
+                     void *workspace, size_t workspace_bytes, unsigned flags, geom_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Point-to-triangle search.
+ * Replaces: TriDistanceKernelLauncher(b,n,xyz,m,tri1,tri2,tri3,dist,point,index)
+ *           tri_distance/tri_distance.cu:213-228 (bound from tri_distance.cpp:16-30).
+ * For every point of xyz (B,n,3) over the m triangles (tri1,tri2,tri3 = per-face vertices A,B,C,
+ * each (B,m,3)): dist = squared distance to the closest triangle as the reference kernel ranks
+ * them, point = region code 0..6 (0 interior, 1/2/3 vertex A/B/C, 4/5/6 edge AB/BC/CA),
+ * index = face index.  Arithmetic and quirks (option-6 direction vector, NaN tile poisoning,
+ * best=10000 initialisation) follow tri_distance.cu:124-206 as compiled; see DESIGN.md.
+ * No workspace.
+ * ------------------------------------------------------------------------------------------- */
+GEOM_API int geom_tri_fwd(int b, int n, const float *xyz, int m, const float *tri1, const float *tri2,
+                 const float *tri3, float *dist, int *point, int *index,
+                 unsigned flags, geom_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GEOM_B200_H */
