@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: Chamfer point-pairs/s on 32 x (10000 vs 10000) fp32 (BASELINE
+config 2), one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" is one ChamferDistance nearest-neighbour search (both directions, the reference's
+ChamferDistanceKernelLauncher, chamfer_distance.cu:57-73) over one batch of 32 point-set pairs per
+GPU (weak scaling: the batch axis shards with no data-path collective).  point-pairs
+per step = B*n*m = 3.2e9 per GPU.
+
+Output: one JSON line (rank 0).  `value` = device-resident throughput (CUDA events, max over ranks);
+`e2e` = the same metric through the public API with pinned HOST buffers, H2D/D2H copies inside the
+timed region; `roofline` = algorithmic HBM bytes of the dominant kernel / its measured duration vs
+MEASURED_PEAKS.json (the search is FP32-issue bound, see DESIGN.md: the FP32 fraction is reported
+beside it); `cpu_baseline` = the reference's own CPU nnsearch (oracle/_ref/libref_cpu.so, else the
+oracle port) on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+B, N_PTS, M_PTS, SEED = 32, 10000, 10000, 41
+METRIC = "chamfer_point_pairs_per_sec"
+UNIT = "point-pairs/s"
+WORKLOAD = "ChamferDistance 32x(10000 vs 10000) fp32 NN search, both directions (BASELINE configs[1])"
+RING = 24  # distinct input/output sets cycled through so the working set (24 x 15.4 MB) exceeds L2
+
+
+def _config(n_gpus):
+    return {"workload": WORKLOAD, "batch_per_gpu": B, "n": N_PTS, "m": M_PTS, "seed": SEED,
+            "global_batch": B * n_gpus, "parallelism": f"batch-sharded x{n_gpus}, no data-path collective",
+            "l2_policy": f"ring of {RING} distinct input/output/workspace sets (~370 MB > 126 MB L2), no reuse between consecutive steps"}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the reference's nnsearch (old_GEOMetrics/chamfer_distance/src/my_lib.c:4-26)
+# ------------------------------------------------------------------------------------------------
+class CpuBaseline:
+    """Times the reference CPU path.  This (and smoke()/tests) is the only place oracle/ is used."""
+
+    def __init__(self):
+        from oracle import Oracle, RefCpu, have_ref_cpu
+
+        if have_ref_cpu():
+            self.kind, self._search = "reference", RefCpu().nnsearch
+        else:
+            orc = Oracle()
+            self.kind, self._search = "port", lambda a, b, d=None, i=None: orc.nnsearch(a, b)
+        self.threads = max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+
+    def _item(self, x1, x2):
+        # both directions, as nnd_forward does (my_lib.c:42-43); one batch item per call
+        self._search(x1, x2)
+        self._search(x2, x1)
+
+    def run(self, x1, x2, items, threads):
+        """Search `items` batch items (cycled from x1/x2) on `threads` threads; -> seconds."""
+        import numpy as np
+
+        pairs = [(np.ascontiguousarray(x1[k % len(x1)][None]), np.ascontiguousarray(x2[k % len(x2)][None]))
+                 for k in range(items)]
+        nxt = [0]
+        lock = threading.Lock()
+
+        def work():
+            while True:
+                with lock:
+                    k = nxt[0]
+                    nxt[0] += 1
+                if k >= items:
+                    return
+                self._item(*pairs[k])  # ctypes releases the GIL
+
+        t0 = time.perf_counter()
+        ts = [threading.Thread(target=work) for _ in range(min(threads, items))]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        return time.perf_counter() - t0
+
+
+def _host_inputs(seed):
+    from geometrics_b200 import synth
+
+    return synth.random_points(B, N_PTS, seed), synth.random_points(B, M_PTS, seed + 1000)
+
+
+def cpu_baseline_block(budget_s=12.0):
+    cb = CpuBaseline()
+    x1, x2 = _host_inputs(SEED)
+    x1, x2 = x1.numpy(), x2.numpy()
+    t1 = cb.run(x1, x2, 1, 1)  # one item, one thread: how the reference itself runs it
+    items = int(max(cb.threads, min(4 * B, budget_s / max(t1, 1e-3) * cb.threads)))
+    t = cb.run(x1, x2, items, cb.threads)
+    return {
+        "value": items * N_PTS * M_PTS / t, "unit": UNIT, "cores": cb.threads, "kind": cb.kind,
+        "sample": f"{items} batch items of the workload (each 10000 vs 10000, both directions) over {cb.threads} threads, {t:.2f} s",
+        "single_thread_value": N_PTS * M_PTS / t1, "single_thread_sample": f"1 batch item, 1 thread, {t1:.3f} s",
+        "source": "old_GEOMetrics/chamfer_distance/src/my_lib.c nnsearch compiled unmodified (gcc -O3)" if cb.kind == "reference"
+                  else "oracle/chamfer_oracle.c oracle_nnsearch (restatement of my_lib.c:4-26)",
+    }
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = CpuBaseline()
+    x1, x2 = _host_inputs(SEED)
+    x1, x2 = x1.numpy(), x2.numpy()
+    t1 = cb.run(x1, x2, 1, 1)
+    # size the per-step sample so that the whole run stays within ~2 minutes
+    per_step = 120.0 / max(1, args.steps + args.warmup)
+    items = int(max(1, min(B, per_step / max(t1, 1e-3) * cb.threads)))
+    for _ in range(args.warmup):
+        cb.run(x1, x2, items, cb.threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cb.run(x1, x2, items, cb.threads)
+    dt = (time.perf_counter() - t0) / max(1, args.steps)
+    value = items * N_PTS * M_PTS / dt
+    sample = f"{items} of the {B} batch items per step over {cb.threads} host threads (each 10000 vs 10000, both directions)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": _config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cb.threads, "kind": cb.kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region (pynvml thread; nvidia-smi fallback)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz, self._stop = [], set(), None, threading.Event()
+        self._h = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._h = None
+        self._t = threading.Thread(target=self._loop, daemon=True)
+
+    def _loop(self):
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.005)
+
+    def start(self):
+        if self._h is not None:
+            self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._h is not None and self._t.is_alive():
+            self._t.join()
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def _physical_gpu_index(local_rank):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+# ------------------------------------------------------------------------------------------------
+# product arm
+# ------------------------------------------------------------------------------------------------
+def run_product(args):
+    import torch
+    import torch.distributed as dist
+
+    import geometrics_b200 as g
+    from geometrics_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    L = g.lib()
+    stream = torch.cuda.current_stream(dev)
+    sp = stream.cuda_stream
+
+    # ---- inputs: a ring of distinct sets (rank-dependent seeds), resident in HBM ----
+    ring = []
+    ws_bytes = L.geom_chamfer_workspace_bytes(B, N_PTS, M_PTS)
+    for r in range(RING):
+        x1, x2 = _host_inputs(SEED + 7 * r + 100000 * rank)
+        ring.append(dict(
+            x1=x1.to(dev), x2=x2.to(dev),
+            i1=torch.empty(B, N_PTS, dtype=torch.int32, device=dev), i2=torch.empty(B, M_PTS, dtype=torch.int32, device=dev),
+            ws=torch.empty(ws_bytes // 8, dtype=torch.int64, device=dev)))
+
+    def step(k):
+        s = ring[k % RING]
+        # indices only, as chamfer_distance.py:31 returns (dist pointers NULL)
+        st = L.geom_chamfer_fwd(B, N_PTS, s["x1"].data_ptr(), M_PTS, s["x2"].data_ptr(), None, s["i1"].data_ptr(),
+                                None, s["i2"].data_ptr(), s["ws"].data_ptr(), ws_bytes, 0, sp)
+        if st != 0:
+            _lib.check(st, "geom_chamfer_fwd")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for k in range(args.warmup):
+        step(k)
+    barrier()
+    sampler = ClockSampler(_physical_gpu_index(local))
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for k in range(args.steps):
+        step(args.warmup + k)
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+
+    # ---- second pass of the same K steps with the library's per-kernel event timing on: average
+    #      launch duration of each kernel over the timed region, on the launch stream ----
+    _lib.prof_begin()
+    for k in range(args.steps):
+        step(args.warmup + k)
+    kern = _lib.prof_end()  # {name: (total ms, launches)}
+    barrier()
+    dom_name = max(kern, key=lambda k_: kern[k_][0])
+    kern_ms = kern[dom_name][0] / kern[dom_name][1]
+    launches = sum(c for _, c in kern.values())
+
+    # ---- end to end: pinned host buffers in, indices out, copies inside the timed region ----
+    hx1, hx2 = _host_inputs(SEED + 100000 * rank)
+    hx1, hx2 = hx1.pin_memory(), hx2.pin_memory()
+    hi1 = torch.empty(B, N_PTS, dtype=torch.int32).pin_memory()
+    hi2 = torch.empty(B, M_PTS, dtype=torch.int32).pin_memory()
+    e2e_steps = max(3, min(args.steps, 30))
+    for _ in range(2):
+        g.chamfer_forward_host(hx1, hx2, hi1, hi2, device=dev)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        g.chamfer_forward_host(hx1, hx2, hi1, hi2, device=dev)  # returns after the D2H copy completed
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+
+    # ---- reduce over ranks (max time) ----
+    t = torch.tensor([ms_total, e2e_s, kern_ms or 0.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_s, kern_ms_max = (float(v) for v in t.tolist())
+    ms_step = ms_total / args.steps
+    pairs_step = B * N_PTS * M_PTS * world
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        alg_bytes = 16 * B * (N_PTS + M_PTS)  # read 12 B/point, write one int32 index/point
+        dom_ms = kern_ms_max
+        ach = alg_bytes / (dom_ms * 1e-3) / 1e9
+        sm_mhz = clocks.get("sm_mhz") or 1965
+        fp32_peak = 148 * 128 * sm_mhz * 1e6  # FP32 lane-ops/s at the clock observed under load
+        lane_ops = 6 * B * N_PTS * M_PTS      # 3 sub + 1 mul + 2 fma per pair, each pair evaluated once
+        out = {
+            "metric": METRIC, "value": pairs_step / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": _config(world),
+            "clocks": clocks,
+            "e2e": {"value": pairs_step / e2e_s, "unit": UNIT, "h2d_bytes_per_step": hx1.numel() * 4 + hx2.numel() * 4,
+                    "d2h_bytes_per_step": hi1.numel() * 4 + hi2.numel() * 4, "ms_per_step": e2e_s * 1e3,
+                    "api": "geometrics_b200.chamfer_forward_host (pinned host in/out)", "steps": e2e_steps},
+            "gpu_launches": launches,
+            "kernels": {k_: {"ms_per_launch": v[0] / v[1], "launches": v[1], "share_of_step": v[0] / args.steps / ms_step}
+                        for k_, v in kern.items()},
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                         "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
+                         "kernel": dom_name, "kernel_ms": dom_ms, "algorithmic_bytes": alg_bytes,
+                         "note": "brute-force NN is FP32-issue bound, not HBM bound (SURVEY.md 8d); see fp32 below",
+                         "fp32": {"lane_ops_per_launch": lane_ops, "achieved_tlops": lane_ops / (dom_ms * 1e-3) / 1e12,
+                                  "peak_tlops": fp32_peak / 1e12, "frac": lane_ops / (dom_ms * 1e-3) / fp32_peak,
+                                  "peak_source": f"148 SM x 128 FP32 lanes x {sm_mhz} MHz (median SM clock during the run)"}},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline_block()
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="product", choices=["product", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "product" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_product(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -24,8 +24,14 @@ SYMBOLS = {
     "geom_abi_version": (_i, []),
     "geom_status_string": (C.c_char_p, [_i]),
     "geom_device_info": (_i, [C.POINTER(_i)] * 3),
+    "geom_prof_begin": (_i, []),
+    "geom_prof_end": (_i, [C.POINTER(C.c_float), C.POINTER(_i)]),
+    "geom_prof_kernel_name": (C.c_char_p, [_i]),
     "geom_chamfer_workspace_bytes": (_sz, [_i, _i, _i]),
     "geom_chamfer_fwd": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _u, _vp]),
+    "geom_chamfer_loss_workspace_bytes": (_sz, [_i, _i, _i]),
+    "geom_chamfer_loss_fwd": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "geom_chamfer_loss_bwd": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "geom_tri_fwd": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _u, _vp]),
 }
 
@@ -63,6 +69,22 @@ def lib() -> C.CDLL:
             raise GeomLibraryError(f"{LIB_PATH} has ABI {L.geom_abi_version()}, expected {GEOM_ABI_VERSION}; rebuild it")
         _lib = L
     return _lib
+
+
+GEOM_PROF_KERNELS = 16
+
+
+def prof_begin() -> None:
+    check(lib().geom_prof_begin(), "geom_prof_begin")
+
+
+def prof_end() -> dict:
+    """-> {kernel name: (total device ms, launches)} for kernels launched since prof_begin()."""
+    ms = (C.c_float * GEOM_PROF_KERNELS)()
+    cnt = (_i * GEOM_PROF_KERNELS)()
+    check(lib().geom_prof_end(ms, cnt), "geom_prof_end")
+    return {lib().geom_prof_kernel_name(k).decode(): (float(ms[k]), int(cnt[k]))
+            for k in range(GEOM_PROF_KERNELS) if cnt[k]}
 
 
 def check(status: int, what: str) -> None:

@@ -21,16 +21,16 @@
 //     work items: no block-level barriers, no tail imbalance, 16 warps/SM.
 //   * Partial results from different workers meet in 64-bit keys (distance bits << 32 | tag) merged
 //     with filtered atomicMin, which also implements "lowest index wins ties".
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace geom {
 namespace chamfer {
 
-constexpr int kR = 8;                   // xyz1 rows per lane
-constexpr int kRowsPerWarp = 32 * kR;   // row block = tag granularity of the column keys
 constexpr int kWarps = 4;
 constexpr int kThreads = 32 * kWarps;
-constexpr int kCtasPerSm = 4;
 constexpr int kMaxTileCols = 256;
 constexpr int kGroupCols = 8;           // tag granularity of the row keys (two 4-column steps)
 constexpr int kRefTile = 512;           // the reference kernel's smem tile (chamfer_distance.cu:15)
@@ -40,60 +40,51 @@ struct TwoWayArgs {
     const float *xyz2;
     u64 *rowkey;  // [b][n_full]
     u64 *colkey;  // [b][m_full]
+    unsigned *ticket;    // work counter, starts at 0xffffffff (part of the 0xff-filled workspace)
     int n, m;            // scanned extents (tail-trimmed in compatibility mode)
     int n_full, m_full;  // real point counts = array strides
     int n_rblk, n_ctile, tile_cols;
-    long long total_tiles;
+    int strip;           // column tiles per work unit
+    int strips_per_row;  // ceil(n_ctile / strip)
+    unsigned total_units;
 };
 
-__device__ __forceinline__ void flush_rows(const TwoWayArgs &a, long long rid, int lane,
-                                           const float (&best)[kR], const unsigned (&grp)[kR])
+// One warp = one worker.  Work units (row block of 32*R xyz1 rows) x (strip of column tiles) are
+// handed out by a global ticket counter, so every warp stays busy until the whole search is done
+// (a static split leaves the SM sub-partitions' lower-priority warps running alone at the end).
+template <int R, int MINB, int TILE>
+__global__ void __launch_bounds__(kThreads, MINB) twoway_kernel(const TwoWayArgs a)
 {
-    const int bi = (int)(rid / a.n_rblk);
-    const int rbase = (int)(rid % a.n_rblk) * kRowsPerWarp;
-    u64 *rk = a.rowkey + (size_t)bi * a.n_full;
-#pragma unroll
-    for (int r = 0; r < kR; ++r) {
-        const int row = rbase + r * 32 + lane;
-        if (row < a.n) key_min(&rk[row], make_key(best[r], grp[r]));
-    }
-}
-
-__global__ void __launch_bounds__(kThreads, kCtasPerSm) twoway_kernel(const TwoWayArgs a)
-{
+    constexpr int kRowsPerWarp = 32 * R;
     // Per-warp private staging: candidate tile as duplicated SoA pairs {v,v} so one 64-bit register
     // pair feeds a packed op against two different rows; and the tile's column minima.
-    __shared__ __align__(16) float2 s_q[kWarps][3][kMaxTileCols];
-    __shared__ __align__(16) unsigned s_col[kWarps][kMaxTileCols];
+    __shared__ __align__(16) float2 s_q[kWarps][3][TILE];
+    __shared__ __align__(16) unsigned s_col[kWarps][TILE];
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    float2(*sq)[kMaxTileCols] = s_q[warp];
+    float2(*sq)[TILE] = s_q[warp];
     unsigned *scol = s_col[warp];
 
-    const long long slot = (long long)blockIdx.x * kWarps + warp;
-    const long long nslots = (long long)gridDim.x * kWarps;
-    const long long t0 = a.total_tiles * slot / nslots;
-    const long long t1 = a.total_tiles * (slot + 1) / nslots;
+    u64 nx[R / 2], ny[R / 2], nz[R / 2];  // negated row coordinates, rows (2i, 2i+1) packed
+    float best[R];
+    unsigned grp[R];
 
-    u64 nx[kR / 2], ny[kR / 2], nz[kR / 2];  // negated row coordinates, rows (2i, 2i+1) packed
-    float best[kR];
-    unsigned grp[kR];
-    long long cur_rid = -1;
-    int bi = 0, rb = 0;
-
-    for (long long t = t0; t < t1; ++t) {
-        const int ct = (int)(t % a.n_ctile);
-        const long long rid = t / a.n_ctile;
-        if (rid != cur_rid) {
-            if (cur_rid >= 0) flush_rows(a, cur_rid, lane, best, grp);
-            cur_rid = rid;
-            bi = (int)(rid / a.n_rblk);
-            rb = (int)(rid % a.n_rblk);
+    for (;;) {
+        unsigned u = 0;
+        if (lane == 0) u = atomicAdd(a.ticket, 1u) + 1u;
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= a.total_units) break;
+        const unsigned rid = u / (unsigned)a.strips_per_row;
+        const int ct0 = (int)(u % (unsigned)a.strips_per_row) * a.strip;
+        const int ct1 = min(ct0 + a.strip, a.n_ctile);
+        const int bi = (int)(rid / (unsigned)a.n_rblk);
+        const int rb = (int)(rid % (unsigned)a.n_rblk);
+        const int rbase = rb * kRowsPerWarp;
+        {
             const float *p1 = a.xyz1 + (size_t)bi * a.n_full * 3;
-            const int rbase = rb * kRowsPerWarp;
 #pragma unroll
-            for (int i = 0; i < kR / 2; ++i) {
+            for (int i = 0; i < R / 2; ++i) {
                 // rows past the end are clamped duplicates: they add no new values to any minimum
                 const int r0 = min(rbase + (2 * i) * 32 + lane, a.n - 1);
                 const int r1 = min(rbase + (2 * i + 1) * 32 + lane, a.n - 1);
@@ -102,92 +93,105 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) twoway_kernel(const TwoW
                 nz[i] = pack2(-p1[r0 * 3 + 2], -p1[r1 * 3 + 2]);
             }
 #pragma unroll
-            for (int r = 0; r < kR; ++r) {
+            for (int r = 0; r < R; ++r) {
                 best[r] = __int_as_float(0x7f800000);
                 grp[r] = 0u;
             }
         }
 
-        // ---- stage the candidate tile ----
-        const int c0 = ct * a.tile_cols;
-        const int tc = min(a.tile_cols, a.m - c0);
-        const int ngroups = (tc + kGroupCols - 1) / kGroupCols;
-        {
-            const float *p2 = a.xyz2 + ((size_t)bi * a.m_full + c0) * 3;
-            const int nel = ngroups * kGroupCols * 3;
-            for (int e = lane; e < nel; e += 32) {
-                const int pt = e / 3;
-                const int c = e - pt * 3;
-                const float v = p2[min(pt, tc - 1) * 3 + c];  // padding = duplicate of the last column
-                sq[c][pt] = make_float2(v, v);
+        for (int ct = ct0; ct < ct1; ++ct) {
+            // ---- stage the candidate tile ----
+            const int c0 = ct * a.tile_cols;
+            const int tc = min(a.tile_cols, a.m - c0);
+            const int ngroups = (tc + kGroupCols - 1) / kGroupCols;
+            {
+                const float *p2 = a.xyz2 + ((size_t)bi * a.m_full + c0) * 3;
+                const int nel = ngroups * kGroupCols * 3;
+                for (int e = lane; e < nel; e += 32) {
+                    const int pt = e / 3;
+                    const int c = e - pt * 3;
+                    const float v = p2[min(pt, tc - 1) * 3 + c];  // padding = duplicate of the last column
+                    sq[c][pt] = make_float2(v, v);
+                }
             }
-        }
-        __syncwarp();
+            __syncwarp();
 
-        // ---- all pairs of (256 rows) x (tile columns) ----
-        const unsigned gid0 = (unsigned)(c0 / kGroupCols);
+            // ---- all pairs of (32*R rows) x (tile columns) ----
+            const unsigned gid0 = (unsigned)(c0 / kGroupCols);
 #pragma unroll 1
-        for (int g = 0; g < ngroups; ++g) {
-            float nb[kR];
+            for (int g = 0; g < ngroups; ++g) {
+                float nb[R];
 #pragma unroll
-            for (int r = 0; r < kR; ++r) nb[r] = best[r];
+                for (int r = 0; r < R; ++r) nb[r] = best[r];
 #pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                const int col = g * kGroupCols + s * 4;
-                const ulonglong2 xa = *reinterpret_cast<const ulonglong2 *>(&sq[0][col]);
-                const ulonglong2 xb = *reinterpret_cast<const ulonglong2 *>(&sq[0][col + 2]);
-                const ulonglong2 ya = *reinterpret_cast<const ulonglong2 *>(&sq[1][col]);
-                const ulonglong2 yb = *reinterpret_cast<const ulonglong2 *>(&sq[1][col + 2]);
-                const ulonglong2 za = *reinterpret_cast<const ulonglong2 *>(&sq[2][col]);
-                const ulonglong2 zb = *reinterpret_cast<const ulonglong2 *>(&sq[2][col + 2]);
-                const u64 qx[4] = {xa.x, xa.y, xb.x, xb.y};
-                const u64 qy[4] = {ya.x, ya.y, yb.x, yb.y};
-                const u64 qz[4] = {za.x, za.y, zb.x, zb.y};
-                float d[4][kR];  // [column][row]
+                for (int s = 0; s < 2; ++s) {
+                    const int col = g * kGroupCols + s * 4;
+                    const ulonglong2 xa = *reinterpret_cast<const ulonglong2 *>(&sq[0][col]);
+                    const ulonglong2 xb = *reinterpret_cast<const ulonglong2 *>(&sq[0][col + 2]);
+                    const ulonglong2 ya = *reinterpret_cast<const ulonglong2 *>(&sq[1][col]);
+                    const ulonglong2 yb = *reinterpret_cast<const ulonglong2 *>(&sq[1][col + 2]);
+                    const ulonglong2 za = *reinterpret_cast<const ulonglong2 *>(&sq[2][col]);
+                    const ulonglong2 zb = *reinterpret_cast<const ulonglong2 *>(&sq[2][col + 2]);
+                    const u64 qx[4] = {xa.x, xa.y, xb.x, xb.y};
+                    const u64 qy[4] = {ya.x, ya.y, yb.x, yb.y};
+                    const u64 qz[4] = {za.x, za.y, zb.x, zb.y};
+                    float d[4][R];  // [column][row]
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                    for (int c = 0; c < 4; ++c) {
 #pragma unroll
-                    for (int i = 0; i < kR / 2; ++i) {
-                        const u64 dx = add2(qx[c], nx[i]);
-                        const u64 dy = add2(qy[c], ny[i]);
-                        const u64 dz = add2(qz[c], nz[i]);
-                        const u64 dd = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
-                        unpack2(dd, d[c][2 * i], d[c][2 * i + 1]);
+                        for (int i = 0; i < R / 2; ++i) {
+                            const u64 dx = add2(qx[c], nx[i]);
+                            const u64 dy = add2(qy[c], ny[i]);
+                            const u64 dz = add2(qz[c], nz[i]);
+                            const u64 dd = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
+                            unpack2(dd, d[c][2 * i], d[c][2 * i + 1]);
+                        }
                     }
-                }
 #pragma unroll
-                for (int r = 0; r < kR; ++r) {
-                    nb[r] = min3(nb[r], d[0][r], d[1][r]);
-                    nb[r] = min3(nb[r], d[2][r], d[3][r]);
-                }
-                unsigned cv[4];
+                    for (int r = 0; r < R; ++r) {
+                        nb[r] = min3(nb[r], d[0][r], d[1][r]);
+                        nb[r] = min3(nb[r], d[2][r], d[3][r]);
+                    }
+                    unsigned cv[4];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    float cm = min3(d[c][0], d[c][1], d[c][2]);
-                    cm = min3(cm, d[c][3], d[c][4]);
-                    cm = min3(cm, d[c][5], d[c][6]);
-                    cm = fminf(cm, d[c][7]);
-                    cv[c] = __reduce_min_sync(0xffffffffu, __float_as_uint(cm));
+                    for (int c = 0; c < 4; ++c) {
+                        float cm = min3(d[c][0], d[c][1], d[c][2]);
+                        if (R == 4) {
+                            cm = fminf(cm, d[c][3]);
+                        } else {
+#pragma unroll
+                            for (int r = 3; r + 1 < R; r += 2) cm = min3(cm, d[c][r], d[c][r + 1]);
+                            cm = fminf(cm, d[c][R - 1]);
+                        }
+                        cv[c] = __reduce_min_sync(0xffffffffu, __float_as_uint(cm));
+                    }
+                    if (lane == 0) *reinterpret_cast<uint4 *>(&scol[col]) = make_uint4(cv[0], cv[1], cv[2], cv[3]);
                 }
-                if (lane == 0) *reinterpret_cast<uint4 *>(&scol[col]) = make_uint4(cv[0], cv[1], cv[2], cv[3]);
+                const unsigned gid = gid0 + (unsigned)g;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    grp[r] = (nb[r] < best[r]) ? gid : grp[r];
+                    best[r] = nb[r];
+                }
             }
-            const unsigned gid = gid0 + (unsigned)g;
-#pragma unroll
-            for (int r = 0; r < kR; ++r) {
-                grp[r] = (nb[r] < best[r]) ? gid : grp[r];
-                best[r] = nb[r];
-            }
-        }
-        __syncwarp();
+            __syncwarp();
 
-        // ---- publish the tile's column minima ----
-        {
-            u64 *ck = a.colkey + (size_t)bi * a.m_full + c0;
-            for (int cc = lane; cc < tc; cc += 32) key_min(&ck[cc], ((u64)scol[cc] << 32) | (u64)(unsigned)rb);
+            // ---- publish the tile's column minima ----
+            {
+                u64 *ck = a.colkey + (size_t)bi * a.m_full + c0;
+                for (int cc = lane; cc < tc; cc += 32) key_min(&ck[cc], ((u64)scol[cc] << 32) | (u64)(unsigned)rb);
+            }
+            __syncwarp();
         }
-        __syncwarp();
+
+        // ---- publish this strip's row minima ----
+        u64 *rk = a.rowkey + (size_t)bi * a.n_full;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int row = rbase + r * 32 + lane;
+            if (row < a.n) key_min(&rk[row], make_key(best[r], grp[r]));
+        }
     }
-    if (cur_rid >= 0) flush_rows(a, cur_rid, lane, best, grp);
 }
 
 struct RefineArgs {
@@ -200,17 +204,21 @@ struct RefineArgs {
     float *dist2;
     int *idx2;
     int b, n, m, n_full, m_full;
-    int zero1, zero2;  // reference "empty final tile" behaviour, see geom_chamfer_fwd
+    int rows_per_warp;  // column-key tag granularity (32 * R of the search kernel that ran)
+    int zero1, zero2;   // reference "empty final tile" behaviour, see geom_chamfer_fwd
 };
 
 // Recover exact indices from (minimum distance, coarse tag): re-evaluate the tagged candidates in
 // ascending order and take the first whose distance equals the minimum bit for bit.
-__global__ void __launch_bounds__(256) refine_kernel(const RefineArgs a)
+//   blocks [0, row_blocks): one thread per xyz1 row, 8 tagged columns (96 contiguous bytes);
+//   the rest: one warp per xyz2 column, the 256 tagged rows 32 at a time (coalesced), first hit by ballot.
+constexpr int kRefineThreads = 256;
+
+__global__ void __launch_bounds__(kRefineThreads) refine_kernel(const RefineArgs a, int row_blocks)
 {
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long nrows = (long long)a.b * a.n;
-    const long long ncols = (long long)a.b * a.m;
-    if (gid < nrows) {
+    if ((int)blockIdx.x < row_blocks) {
+        const long long gid = (long long)blockIdx.x * kRefineThreads + threadIdx.x;
+        if (gid >= (long long)a.b * a.n) return;
         const int bi = (int)(gid / a.n), j = (int)(gid % a.n);
         const u64 key = a.rowkey[(size_t)bi * a.n_full + j];
         float dmin = __uint_as_float((unsigned)(key >> 32));
@@ -232,23 +240,31 @@ __global__ void __launch_bounds__(256) refine_kernel(const RefineArgs a)
         }
         if (a.dist1) a.dist1[(size_t)bi * a.n_full + j] = dmin;
         a.idx1[(size_t)bi * a.n_full + j] = idx;
-    } else if (gid - nrows < ncols) {
-        const long long g2 = gid - nrows;
-        const int bi = (int)(g2 / a.m), k = (int)(g2 % a.m);
-        const u64 key = a.colkey[(size_t)bi * a.m_full + k];
-        float dmin = __uint_as_float((unsigned)(key >> 32));
-        const int rb0 = (int)(unsigned)key * kRowsPerWarp;
-        const int re = min(rb0 + kRowsPerWarp, a.n);
-        const float *q = a.xyz2 + ((size_t)bi * a.m_full + k) * 3;
-        const float *cand = a.xyz1 + (size_t)bi * a.n_full * 3;
-        const float qx = q[0], qy = q[1], qz = q[2];
-        int idx = rb0;
-        for (int r = rb0; r < re; ++r) {
-            if (sqdist_ref(qx, qy, qz, cand[r * 3 + 0], cand[r * 3 + 1], cand[r * 3 + 2]) == dmin) {
-                idx = r;
-                break;
-            }
+        return;
+    }
+    const int lane = threadIdx.x & 31;
+    const long long g2 = ((long long)blockIdx.x - row_blocks) * (kRefineThreads / 32) + (threadIdx.x >> 5);
+    if (g2 >= (long long)a.b * a.m) return;
+    const int bi = (int)(g2 / a.m), k = (int)(g2 % a.m);
+    const u64 key = a.colkey[(size_t)bi * a.m_full + k];
+    float dmin = __uint_as_float((unsigned)(key >> 32));
+    const int rb0 = (int)(unsigned)key * a.rows_per_warp;
+    const float *q = a.xyz2 + ((size_t)bi * a.m_full + k) * 3;
+    const float *cand = a.xyz1 + (size_t)bi * a.n_full * 3;
+    const float qx = q[0], qy = q[1], qz = q[2];
+    int idx = rb0;
+#pragma unroll 2
+    for (int r0 = rb0; r0 < min(rb0 + a.rows_per_warp, a.n); r0 += 32) {
+        const int r = r0 + lane;
+        bool hit = false;
+        if (r < a.n) hit = sqdist_ref(qx, qy, qz, cand[r * 3 + 0], cand[r * 3 + 1], cand[r * 3 + 2]) == dmin;
+        const unsigned mask = __ballot_sync(0xffffffffu, hit);
+        if (mask) {
+            idx = r0 + __ffs(mask) - 1;
+            break;
         }
+    }
+    if (lane == 0) {
         if (a.zero2 && dmin > 0.0f) {
             dmin = 0.0f;
             idx = 0;
@@ -330,7 +346,10 @@ static cudaError_t launch_oneway(int b, const float *q, int q_full, int q0, int 
     if (nq <= 0 || b <= 0) return cudaSuccess;
     const int per_cta = kOneWayThreads * kOneWayQR;
     dim3 grid((nq + per_cta - 1) / per_cta, b);
-    oneway_kernel<<<grid, kOneWayThreads, 0, st>>>(q, q_full, q0, nq, c, c_full, mc, dist, idx, zero);
+    {
+        prof::Scope ps(st, prof::kChamferOneWay);
+        oneway_kernel<<<grid, kOneWayThreads, 0, st>>>(q, q_full, q0, nq, c, c_full, mc, dist, idx, zero);
+    }
     return cudaGetLastError();
 }
 
@@ -345,6 +364,22 @@ static cudaError_t fill_zero(int b, int cnt, float *dist, int *idx, cudaStream_t
     return e;
 }
 
+struct Tune {
+    int variant, strip, tile_cols;
+};
+static Tune read_tune()
+{
+    Tune t = {0, 2, 0};
+    if (const char *e = getenv("GEOM_CHAMFER_TUNE")) {
+        int v = 0, s = 0, tc = 0;
+        const int got = sscanf(e, "%d,%d,%d", &v, &s, &tc);
+        if (got >= 1 && v >= 0 && v < 5) t.variant = v;
+        if (got >= 2 && s >= 1) t.strip = s;
+        if (got >= 3 && tc >= 32) t.tile_cols = tc;
+    }
+    return t;
+}
+
 }  // namespace chamfer
 }  // namespace geom
 
@@ -353,7 +388,7 @@ using namespace geom;
 extern "C" size_t geom_chamfer_workspace_bytes(int b, int n, int m)
 {
     if (b < 0 || n < 0 || m < 0) return 0;
-    return sizeof(u64) * (size_t)b * ((size_t)n + (size_t)m);
+    return sizeof(u64) * (size_t)b * ((size_t)n + (size_t)m) + 16;  // keys + the work ticket
 }
 
 extern "C" int geom_chamfer_fwd(int b, int n, const float *xyz1, int m, const float *xyz2,
@@ -387,31 +422,56 @@ extern "C" int geom_chamfer_fwd(int b, int n, const float *xyz1, int m, const fl
         if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess)
             return status_from_cuda(e);
 
+        // Kernel variant: rows per lane R, resident CTAs per SM, widest column tile.  The default was
+        // picked on B200 (profiles/); GEOM_CHAMFER_TUNE="variant,strip,tile_cols" overrides for tuning.
+        struct Variant {
+            int rows_per_lane, ctas_per_sm, max_tile;
+            void (*kernel)(const TwoWayArgs);
+        };
+        static const Variant kVariants[] = {
+            {8, 4, 256, twoway_kernel<8, 4, 256>},
+            {4, 8, 128, twoway_kernel<4, 8, 128>},
+            {4, 6, 256, twoway_kernel<4, 6, 256>},
+            {8, 3, 256, twoway_kernel<8, 3, 256>},
+            {6, 5, 256, twoway_kernel<6, 5, 256>},
+        };
+        static const Tune tune = read_tune();
+        const Variant &v = kVariants[tune.variant];
+        const int rows_per_warp = 32 * v.rows_per_lane;
+
         TwoWayArgs a;
         a.xyz1 = xyz1;
         a.xyz2 = xyz2;
         a.rowkey = (u64 *)workspace;
         a.colkey = a.rowkey + (size_t)b * n;
+        a.ticket = (unsigned *)(a.colkey + (size_t)b * m);
         a.n = n_scan;
         a.m = m_scan;
         a.n_full = n;
         a.m_full = m;
-        a.n_rblk = (n_scan + kRowsPerWarp - 1) / kRowsPerWarp;
-        int ctas = sms * kCtasPerSm;
+        a.n_rblk = (n_scan + rows_per_warp - 1) / rows_per_warp;
+        int ctas = sms * v.ctas_per_sm;
         const long long slots = (long long)ctas * kWarps;
-        // widest column tile that still leaves every worker >= 8 tiles (load balance: +-1 tile)
-        int tile_cols = kMaxTileCols;
+        // widest column tile that still gives every worker >= 8 tiles to pull
+        int tile_cols = tune.tile_cols > 0 ? min(tune.tile_cols, v.max_tile) : v.max_tile;
         for (; tile_cols > 32; tile_cols >>= 1) {
             const long long tiles = (long long)b * a.n_rblk * ((m_scan + tile_cols - 1) / tile_cols);
             if (tiles >= 8 * slots) break;
         }
         a.tile_cols = tile_cols;
         a.n_ctile = (m_scan + tile_cols - 1) / tile_cols;
-        a.total_tiles = (long long)b * a.n_rblk * a.n_ctile;
-        if (a.total_tiles < slots) ctas = (int)((a.total_tiles + kWarps - 1) / kWarps);
+        a.strip = max(1, min(tune.strip, a.n_ctile));
+        a.strips_per_row = (a.n_ctile + a.strip - 1) / a.strip;
+        const long long units = (long long)b * a.n_rblk * a.strips_per_row;
+        if (units > 0x7fffffffLL) return GEOM_ERR_INVALID_ARG;
+        a.total_units = (unsigned)units;
+        if (units < slots) ctas = (int)((units + kWarps - 1) / kWarps);
 
         if ((e = cudaMemsetAsync(workspace, 0xff, need, st)) != cudaSuccess) return status_from_cuda(e);
-        twoway_kernel<<<ctas, kThreads, 0, st>>>(a);
+        {
+            prof::Scope ps(st, prof::kChamferTwoWay);
+            v.kernel<<<ctas, kThreads, 0, st>>>(a);
+        }
         if ((e = cudaGetLastError()) != cudaSuccess) return status_from_cuda(e);
 
         RefineArgs r;
@@ -428,10 +488,15 @@ extern "C" int geom_chamfer_fwd(int b, int n, const float *xyz1, int m, const fl
         r.m = m_scan;
         r.n_full = n;
         r.m_full = m;
+        r.rows_per_warp = rows_per_warp;
         r.zero1 = zero1;
         r.zero2 = zero2;
-        const long long items = (long long)b * ((long long)n_scan + m_scan);
-        refine_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(r);
+        const long long row_blocks = ((long long)b * n_scan + kRefineThreads - 1) / kRefineThreads;
+        const long long col_blocks = ((long long)b * m_scan + kRefineThreads / 32 - 1) / (kRefineThreads / 32);
+        {
+            prof::Scope ps(st, prof::kChamferRefine);
+            refine_kernel<<<(unsigned)(row_blocks + col_blocks), kRefineThreads, 0, st>>>(r, (int)row_blocks);
+        }
         if ((e = cudaGetLastError()) != cudaSuccess) return status_from_cuda(e);
 
         // queries beyond the trimmed extents still need an answer over the trimmed candidates

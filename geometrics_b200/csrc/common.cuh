@@ -76,6 +76,22 @@ __device__ __forceinline__ void key_min(u64 *addr, u64 key)
     if (key < cur) atomicMin(addr, key);
 }
 
+// ---- optional per-kernel timing (prof.cu); ids index geom_prof_end()'s arrays ----
+namespace prof {
+enum Kernel {
+    kChamferTwoWay = 0, kChamferRefine, kChamferOneWay, kTri, kChamferLoss, kChamferLossBwd,
+    kSampleFwd, kSampleBwd, kSampleArea, kGcnGemm, kGcnSpmm, kGcnBwd, kTriClosest, kTriClosestBwd,
+    kMisc, kMisc2, kKernelCount
+};
+static_assert(kKernelCount == GEOM_PROF_KERNELS, "geom_b200.h GEOM_PROF_KERNELS out of sync");
+struct Scope {
+    Scope(cudaStream_t st, int id);
+    ~Scope();
+    cudaStream_t st_;
+    int rec_;
+};
+}  // namespace prof
+
 inline int status_from_cuda(cudaError_t e) { return e == cudaSuccess ? GEOM_OK : (int)e; }
 
 }  // namespace geom

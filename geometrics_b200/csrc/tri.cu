@@ -144,9 +144,11 @@ tri_kernel(int n, const float *__restrict__ xyzp, int m, const float *__restrict
         ridx[r] = 0;
     }
 
-    for (int k2 = 0; k2 < m; k2 += kRefTile) {
+    // exact mode is a flat scan (one "tile" spanning every face): no tail skip, no per-tile restart
+    const int ref_tile = exact ? m : kRefTile;
+    for (int k2 = 0; k2 < m; k2 += ref_tile) {
         // reference tile bookkeeping, tri_distance.cu:112,127-134
-        const int end_k = min(m, k2 + kRefTile) - k2;
+        const int end_k = min(m, k2 + ref_tile) - k2;
         const int end_ka = exact ? end_k : end_k - (end_k & 3);
         float best[kPR], bopt[kPR];
         int bidx[kPR];
@@ -226,7 +228,10 @@ extern "C" int geom_tri_fwd(int b, int n, const float *xyz, int m, const float *
     }
     const int per_cta = kThreads * kPR;
     dim3 grid((n + per_cta - 1) / per_cta, b);
-    tri_kernel<<<grid, kThreads, 0, st>>>(n, xyz, m, tri1, tri2, tri3, dist, point, index,
-                                          (flags & GEOM_FLAG_EXACT_TAIL) ? 1 : 0);
+    {
+        prof::Scope ps(st, prof::kTri);
+        tri_kernel<<<grid, kThreads, 0, st>>>(n, xyz, m, tri1, tri2, tri3, dist, point, index,
+                                              (flags & GEOM_FLAG_EXACT_TAIL) ? 1 : 0);
+    }
     return status_from_cuda(cudaGetLastError());
 }

@@ -57,6 +57,16 @@ GEOM_API const char *geom_status_string(int status);
 /* SM count and compute capability of the current device (the library is built for sm_100a only). */
 GEOM_API int geom_device_info(int *sm_count, int *cc_major, int *cc_minor);
 
+/* Optional per-kernel device timing, thread-local to the calling thread (the only state the library
+ * keeps).  Between geom_prof_begin() and geom_prof_end() every kernel this thread launches through
+ * the API is bracketed by CUDA events on its launch stream; geom_prof_end() synchronises on them and
+ * returns, per kernel id, the summed device milliseconds and the launch count (arrays of
+ * GEOM_PROF_KERNELS entries, either may be NULL).  Used by bench.py for the roofline figures. */
+#define GEOM_PROF_KERNELS 16
+GEOM_API int geom_prof_begin(void);
+GEOM_API int geom_prof_end(float *ms_per_kernel, int *launches_per_kernel);
+GEOM_API const char *geom_prof_kernel_name(int id);
+
 /* ---------------------------------------------------------------------------------------------
  * Chamfer nearest-neighbour search.
  * Replaces: ChamferDistanceKernelLauncher(b,n,xyz,m,xyz2,result,result_i,result2,result2_i)
@@ -72,6 +82,29 @@ GEOM_API size_t geom_chamfer_workspace_bytes(int b, int n, int m);
 GEOM_API int geom_chamfer_fwd(int b, int n, const float *xyz1, int m, const float *xyz2,
                      float *dist1, int *idx1, float *dist2, int *idx2,
                      void *workspace, size_t workspace_bytes, unsigned flags, geom_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Chamfer loss on the indices (forward sums and backward scatter).
+ * Replaces the torch chain after chamfer_dist() in utils.py:402-417 (batch_point_to_point) and
+ * utils.py:451-462 (batch_point_to_surface) -- index offsetting, index_select, (a-b)**2, sum, mean --
+ * and its autograd backward (index_add); the legacy C form is nnd_backward,
+ * old_GEOMetrics/chamfer_distance/src/my_lib.c:49-111.
+ *   sums[0] = sum_{i,j} ||xyz2[i, idx1[i,j]] - xyz1[i,j]||^2      (B*n terms)
+ *   sums[1] = sum_{i,k} ||xyz1[i, idx2[i,k]] - xyz2[i,k]||^2      (B*m terms)
+ * accumulated in double, stored as fp32, deterministic.  dist1 (B,n) / dist2 (B,m) optionally
+ * receive the per-point terms (NULL to skip).  The caller turns sums into means (and all-reduces
+ * them across ranks when the batch is sharded).
+ * Backward: for L = weights[0]*sums[0] + weights[1]*sums[1] (weights = 2 floats in DEVICE memory,
+ * so that an upstream autograd scalar needs no host sync) writes dL/dxyz1 into grad1 (B,n,3) and
+ * dL/dxyz2 into grad2 (B,m,3); either may be NULL.  Indices are constants, as in the reference.
+ * ------------------------------------------------------------------------------------------- */
+GEOM_API size_t geom_chamfer_loss_workspace_bytes(int b, int n, int m);
+GEOM_API int geom_chamfer_loss_fwd(int b, int n, const float *xyz1, int m, const float *xyz2,
+                          const int *idx1, const int *idx2, float *dist1, float *dist2, float *sums,
+                          void *workspace, size_t workspace_bytes, geom_stream_t stream);
+GEOM_API int geom_chamfer_loss_bwd(int b, int n, const float *xyz1, int m, const float *xyz2,
+                          const int *idx1, const int *idx2, const float *weights,
+                          float *grad1, float *grad2, geom_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Point-to-triangle search.

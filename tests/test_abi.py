@@ -33,7 +33,7 @@ def test_library_loads_and_reports_version():
     assert L.geom_abi_version() == _lib.GEOM_ABI_VERSION
     assert L.geom_status_string(0) == b"ok"
     assert b"workspace" in L.geom_status_string(-2)
-    assert L.geom_chamfer_workspace_bytes(32, 10000, 10000) == 8 * 32 * 20000
+    assert L.geom_chamfer_workspace_bytes(32, 10000, 10000) == 8 * 32 * 20000 + 16
 
 
 def test_reference_call_surface_names():

@@ -1,0 +1,167 @@
+"""GPU parity tests of geom_chamfer_fwd (through the C ABI via geometrics_b200.chamfer_forward):
+bit-exact distances and indices against (1) the CPU oracle and (2) the reference's own
+chamfer_distance.cu compiled unmodified (oracle/_ref/libref_cuda.so) on the same inputs, plus
+size-independent properties at the BASELINE config-2 size."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import CHAMFER_CASES, chamfer_inputs, assert_same_f32
+
+pytestmark = pytest.mark.gpu
+
+MODES = [dict(), dict(oneway=True), dict(exact_tail=True), dict(exact_tail=True, oneway=True)]
+_ids = lambda c: f"{c[0]}-{c[1]}x{c[2]}x{c[3]}"  # noqa: E731
+
+
+def _run(x1, x2, cuda, **kw):
+    import geometrics_b200 as g
+
+    d1, i1, d2, i2 = g.chamfer_forward(x1.to(cuda), x2.to(cuda), **kw)
+    torch.cuda.synchronize()
+    return d1.cpu().numpy(), i1.cpu().numpy(), d2.cpu().numpy(), i2.cpu().numpy()
+
+
+@pytest.mark.parametrize("mode", MODES, ids=lambda m: "+".join(sorted(m)) or "default")
+@pytest.mark.parametrize("case", CHAMFER_CASES, ids=_ids)
+def test_chamfer_matches_oracle(oracle, cuda, case, mode):
+    x1, x2 = chamfer_inputs(*case)
+    got = _run(x1, x2, cuda, **mode)
+    want = oracle.chamfer_fwd(x1.numpy(), x2.numpy(), exact=mode.get("exact_tail", False))
+    for name, g_, w_ in zip(("dist1", "idx1", "dist2", "idx2"), got, want):
+        if name.startswith("dist"):
+            assert_same_f32(g_, w_, name)
+        else:
+            assert (g_ == w_).all(), f"{name}: {np.count_nonzero(g_ != w_)} of {w_.size} indices differ"
+
+
+@pytest.mark.parametrize("case", CHAMFER_CASES, ids=_ids)
+def test_chamfer_matches_reference_cuda(ref_cuda, cuda, case):
+    """Default mode is bit-compatible with the reference .cu, tail-skip quirks included."""
+    x1, x2 = chamfer_inputs(*case)
+    a, b = x1.to(cuda), x2.to(cuda)
+    rd1, ri1, rd2, ri2 = ref_cuda.chamfer_forward_t(a, b)
+    import geometrics_b200 as g
+
+    d1, i1, d2, i2 = g.chamfer_forward(a, b)
+    torch.cuda.synchronize()
+    assert torch.equal(i1, ri1) and torch.equal(i2, ri2)
+    assert torch.equal(d1, rd1) and torch.equal(d2, rd2)
+
+
+def test_oracle_matches_reference_cuda(oracle, ref_cuda, cuda):
+    """Pins the CPU oracle itself against the reference GPU kernel."""
+    for case in CHAMFER_CASES:
+        x1, x2 = chamfer_inputs(*case)
+        rd1, ri1, rd2, ri2 = ref_cuda.chamfer_forward_t(x1.to(cuda), x2.to(cuda))
+        d1, i1, d2, i2 = oracle.chamfer_fwd(x1.numpy(), x2.numpy())
+        assert (i1 == ri1.cpu().numpy()).all() and (i2 == ri2.cpu().numpy()).all(), case
+        assert_same_f32(d1, rd1.cpu().numpy(), str(case))
+        assert_same_f32(d2, rd2.cpu().numpy(), str(case))
+
+
+def test_module_surface(cuda):
+    """ChamferDistance()(xyz1, xyz2) -> (idx1, idx2): int32, on the inputs' device; accepts a
+    non-contiguous slice (GEOMetrics.py:227 passes gt_samples[:, :2466]) and requires_grad inputs."""
+    from chamfer_distance import ChamferDistance
+    import geometrics_b200 as g
+
+    x1 = (torch.rand(2, 3000, 3, device=cuda) - 0.5).requires_grad_(True)
+    gt = torch.rand(2, 5000, 3, device=cuda) - 0.5
+    idx1, idx2 = ChamferDistance()(gt[:, :2466], x1)
+    assert idx1.dtype == torch.int32 and idx1.shape == (2, 2466) and idx1.device == x1.device
+    assert idx2.dtype == torch.int32 and idx2.shape == (2, 3000)
+    assert not idx1.requires_grad
+    _, e1, _, e2 = g.chamfer_forward(gt[:, :2466].contiguous(), x1.detach())
+    assert torch.equal(idx1, e1) and torch.equal(idx2, e2)
+
+
+def test_argument_errors(cuda):
+    import geometrics_b200 as g
+
+    a = torch.zeros(2, 8, 3, device=cuda)
+    with pytest.raises(ValueError):
+        g.chamfer_forward(a, torch.zeros(3, 8, 3, device=cuda))
+    with pytest.raises(ValueError):
+        g.chamfer_forward(a, torch.zeros(2, 8, 2, device=cuda))
+    with pytest.raises(TypeError):
+        g.chamfer_forward(a, a.double())
+    L = g.lib()
+    # workspace too small -> GEOM_ERR_WORKSPACE, null output -> GEOM_ERR_INVALID_ARG
+    i = torch.zeros(2, 8, dtype=torch.int32, device=cuda)
+    assert L.geom_chamfer_fwd(2, 8, a.data_ptr(), 8, a.data_ptr(), None, i.data_ptr(), None, i.data_ptr(),
+                              None, 0, 0, None) == -2
+    assert L.geom_chamfer_fwd(2, 8, a.data_ptr(), 8, a.data_ptr(), None, None, None, i.data_ptr(),
+                              None, 0, 0, None) == -1
+    assert L.geom_chamfer_fwd(-1, 8, a.data_ptr(), 8, a.data_ptr(), None, i.data_ptr(), None, i.data_ptr(),
+                              None, 0, 0, None) == -1
+
+
+def test_empty_inputs(cuda):
+    import geometrics_b200 as g
+
+    d1, i1, d2, i2 = g.chamfer_forward(torch.zeros(0, 5, 3, device=cuda), torch.zeros(0, 7, 3, device=cuda))
+    assert i1.shape == (0, 5) and i2.shape == (0, 7)
+    # no candidates at all: the reference kernel's tile loop never runs and outputs stay zero
+    d1, i1, d2, i2 = g.chamfer_forward(torch.rand(2, 5, 3, device=cuda), torch.zeros(2, 0, 3, device=cuda))
+    assert (i1 == 0).all() and (d1 == 0).all() and i2.shape == (2, 0)
+
+
+def test_full_size_config2(ref_cuda, cuda):
+    """BASELINE config 2: 32 x (10000 vs 10000), seed 41.  Bit-exact against the reference kernel;
+    plus properties that do not need a second implementation."""
+    from geometrics_b200 import synth
+    import geometrics_b200 as g
+
+    x1 = synth.random_points(32, 10000, 41).to(cuda)
+    x2 = synth.random_points(32, 10000, 42).to(cuda)
+    d1, i1, d2, i2 = g.chamfer_forward(x1, x2)
+    rd1, ri1, rd2, ri2 = ref_cuda.chamfer_forward_t(x1, x2)
+    assert torch.equal(i1, ri1) and torch.equal(i2, ri2)
+    assert torch.equal(d1, rd1) and torch.equal(d2, rd2)
+    _full_size_properties(x1, x2, d1, i1, d2, i2)
+
+
+def _full_size_properties(x1, x2, d1, i1, d2, i2):
+    b, n, _ = x1.shape
+    m = x2.shape[1]
+    assert int(i1.min()) >= 0 and int(i1.max()) < m and int(i2.min()) >= 0 and int(i2.max()) < n
+    # the reported distance is the distance to the reported neighbour (fp32, 1e-5 relative)
+    nn1 = torch.gather(x2, 1, i1.long().unsqueeze(-1).expand(b, n, 3))
+    nn2 = torch.gather(x1, 1, i2.long().unsqueeze(-1).expand(b, m, 3))
+    torch.testing.assert_close(((nn1 - x1) ** 2).sum(-1), d1, rtol=1e-5, atol=1e-12)
+    torch.testing.assert_close(((nn2 - x2) ** 2).sum(-1), d2, rtol=1e-5, atol=1e-12)
+    # minimality on a sample of rows, against torch.cdist-free fp64 brute force
+    rows = torch.arange(0, n, 97, device=x1.device)
+    dd = ((x1[:, rows, None, :].double() - x2[:, None, :, :].double()) ** 2).sum(-1)  # (B, r, m)
+    torch.testing.assert_close(dd.min(-1).values.float(), d1[:, rows], rtol=1e-5, atol=1e-12)
+    # swapping the arguments swaps the outputs bit for bit (d(p,q) is symmetric in fp32)
+    import geometrics_b200 as g
+
+    s1, j1, s2, j2 = g.chamfer_forward(x2, x1)
+    assert torch.equal(j1, i2) and torch.equal(j2, i1) and torch.equal(s1, d2) and torch.equal(s2, d1)
+    # one-way and two-way kernels agree
+    o1, k1, o2, k2 = g.chamfer_forward(x1, x2, oneway=True)
+    assert torch.equal(k1, i1) and torch.equal(k2, i2) and torch.equal(o1, d1) and torch.equal(o2, d2)
+
+
+def test_full_size_properties_without_reference(cuda):
+    """Same properties on tie-heavy lattice data at full size (no reference library needed)."""
+    from geometrics_b200 import synth
+    import geometrics_b200 as g
+
+    x1 = synth.lattice_points(32, 10000, 64, 5).to(cuda)
+    x2 = synth.lattice_points(32, 10000, 64, 6).to(cuda)
+    d1, i1, d2, i2 = g.chamfer_forward(x1, x2)
+    _full_size_properties(x1, x2, d1, i1, d2, i2)
+    # lattice data is exact in fp32: lowest index among ties == first argmin of the exact distances
+    rows = torch.arange(0, 10000, 211, device=cuda)
+    dd = ((x1[:, rows, None, :].double() - x2[:, None, :, :].double()) ** 2).sum(-1)
+    assert torch.equal(dd.argmin(-1).int(), i1[:, rows]) or _first_min_equal(dd, i1[:, rows])
+
+
+def _first_min_equal(dd, idx):
+    # torch.argmin does not promise the first minimum on CUDA; check explicitly
+    mn = dd.min(-1, keepdim=True).values
+    first = (dd == mn).int().argmax(-1)
+    return torch.equal(first.int(), idx)
