@@ -33,6 +33,17 @@ SYMBOLS = {
     "geom_chamfer_loss_fwd": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "geom_chamfer_loss_bwd": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "geom_tri_fwd": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _u, _vp]),
+    "geom_tri_loss_workspace_bytes": (_sz, [_i, _i]),
+    "geom_tri_loss_fwd": (_i, [_i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "geom_tri_loss_bwd": (_i, [_i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "geom_face_areas": (_i, [_i, _i, _vp, _i, _vp, _vp, _i, _vp]),
+    "geom_sample_fwd": (_i, [_i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "geom_sample_bwd": (_i, [_i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "geom_csr_count": (_i, [_i, _vp, _i, _vp, _vp, _vp]),
+    "geom_csr_fill": (_i, [_i, _vp, _i, _vp, _vp, _vp, _vp]),
+    "geom_zeron_gcn_workspace_bytes": (_sz, [_i, _i, _i]),
+    "geom_zeron_gcn_fwd": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
+    "geom_zeron_gcn_bwd_smooth": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 

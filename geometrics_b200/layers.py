@@ -1,0 +1,266 @@
+"""0N-GCN layers with the reference's class names, constructor arguments, parameter names / shapes
+(state-dict compatible with the shipped checkpoints) and ``forward(input, adj, activation)``
+signature (reference ``layers.py``).  ``adj`` is still the dense (V,V) tensor the reference's callers
+hold (``adj_info['adj']``); it is converted once to CSR on the device and cached, and the forward is
+``geom_zeron_gcn_fwd`` (feature GEMM with fused bias / concat + CSR SpMM over the first ``out//split``
+columns) instead of two cuBLAS calls against the dense matrix.  CUDA only.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+from torch.nn.parameter import Parameter
+
+from . import _lib
+
+# ------------------------------------------------------------------------------------------------
+# dense adjacency -> CSR (and CSR of the transpose for the backward), cached per adjacency tensor
+# ------------------------------------------------------------------------------------------------
+_csr_cache: dict = {}
+_CSR_CACHE_MAX = 16
+
+
+class CsrAdjacency:
+    __slots__ = ("V", "nnz", "row_ptr", "col_idx", "val", "t_row_ptr", "t_col_idx", "t_val")
+
+
+def _build_csr(adj: torch.Tensor, transpose: bool):
+    L = _lib.lib()
+    V = adj.shape[0]
+    dev = adj.device
+    sp = _lib.current_stream_ptr(dev)
+    row_cnt = torch.empty(max(V, 1), dtype=torch.int32, device=dev)
+    row_ptr = torch.empty(V + 1, dtype=torch.int32, device=dev)
+    _lib.check(L.geom_csr_count(V, adj.data_ptr(), int(transpose), row_cnt.data_ptr(), row_ptr.data_ptr(), sp), "geom_csr_count")
+    nnz = int(row_ptr[V].item())  # one-time setup sync per adjacency
+    col_idx = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+    val = torch.empty(max(nnz, 1), dtype=torch.float32, device=dev)
+    _lib.check(L.geom_csr_fill(V, adj.data_ptr(), int(transpose), row_ptr.data_ptr(), col_idx.data_ptr(), val.data_ptr(), sp), "geom_csr_fill")
+    return nnz, row_ptr, col_idx, val
+
+
+def csr_from_dense(adj: torch.Tensor) -> CsrAdjacency:
+    """CSR (+ transposed CSR) of a dense (V,V) fp32 CUDA adjacency; cached on (storage, version)."""
+    if adj.dim() != 2 or adj.shape[0] != adj.shape[1]:
+        raise ValueError(f"adj must be a square (V,V) matrix, got {tuple(adj.shape)}")
+    if not adj.is_cuda:
+        raise RuntimeError("adj must be a CUDA tensor (geometrics_b200 has no CPU path)")
+    if adj.dtype != torch.float32:
+        raise TypeError(f"adj must be float32, got {adj.dtype}")
+    key = (adj.data_ptr(), adj._version, adj.shape[0], adj.device.index, adj.is_contiguous())
+    hit = _csr_cache.get(key)
+    if hit is not None:
+        return hit
+    a = adj.detach().contiguous()
+    with torch.cuda.device(a.device):
+        c = CsrAdjacency()
+        c.V = a.shape[0]
+        c.nnz, c.row_ptr, c.col_idx, c.val = _build_csr(a, False)
+        _, c.t_row_ptr, c.t_col_idx, c.t_val = _build_csr(a, True)
+    if len(_csr_cache) >= _CSR_CACHE_MAX:
+        _csr_cache.pop(next(iter(_csr_cache)))
+    _csr_cache[key] = c
+    return c
+
+
+# ------------------------------------------------------------------------------------------------
+# the fused layer
+# ------------------------------------------------------------------------------------------------
+class ZeroNGCNFunction(torch.autograd.Function):
+    """Y = [adj . (XW)[:, :k] | (XW)[:, k:]] + bias for X (B,V,in), W (in,out), k = ksplit."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, csr, ksplit, relu):
+        L = _lib.lib()
+        xc, wc = x.detach().contiguous(), weight.detach().contiguous()
+        bc = bias.detach().contiguous() if bias is not None else None
+        b, v, fin = xc.shape
+        fout = wc.shape[1]
+        dev = xc.device
+        with torch.cuda.device(dev):
+            y = torch.empty((b, v, fout), dtype=torch.float32, device=dev)
+            wsb = L.geom_zeron_gcn_workspace_bytes(b, v, ksplit)
+            ws = torch.empty(max(wsb // 4, 4), dtype=torch.float32, device=dev)
+            _lib.check(L.geom_zeron_gcn_fwd(b, v, fin, fout, ksplit, xc.data_ptr(), wc.data_ptr(),
+                                            bc.data_ptr() if bc is not None else None, csr.row_ptr.data_ptr(),
+                                            csr.col_idx.data_ptr(), csr.val.data_ptr(), y.data_ptr(), int(relu),
+                                            ws.data_ptr(), ws.numel() * 4, _lib.current_stream_ptr(dev)),
+                       "geom_zeron_gcn_fwd")
+        ctx.save_for_backward(xc, wc, y if relu else None)
+        ctx.csr, ctx.ksplit, ctx.has_bias = csr, ksplit, bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, wc, y = ctx.saved_tensors
+        csr, ksplit = ctx.csr, ctx.ksplit
+        L = _lib.lib()
+        dy = dy.contiguous()
+        if y is not None:
+            dy = dy * (y > 0)
+        b, v, fout = dy.shape
+        dev = dy.device
+        with torch.cuda.device(dev):
+            ds = torch.empty_like(dy)
+            _lib.check(L.geom_zeron_gcn_bwd_smooth(b, v, fout, ksplit, csr.t_row_ptr.data_ptr(), csr.t_col_idx.data_ptr(),
+                                                   csr.t_val.data_ptr(), dy.data_ptr(), ds.data_ptr(),
+                                                   _lib.current_stream_ptr(dev)), "geom_zeron_gcn_bwd_smooth")
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.matmul(ds, wc.t())                                   # plain library GEMM
+        if ctx.needs_input_grad[1]:
+            dw = torch.matmul(xc.reshape(-1, xc.shape[-1]).t(), ds.reshape(-1, fout))
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy.sum(dim=(0, 1))
+        return dx, dw, db, None, None, None
+
+
+def zeron_gcn(x, weight, bias, adj, split: int, activation=None):
+    """Functional form.  ``x`` (B,V,in) or (V,in); ``adj`` dense (V,V) or a CsrAdjacency; the first
+    ``out // split`` output columns are neighbour-averaged (split = 3: image GCN, 10: encoder GCN)."""
+    _lib.require_cuda_f32("input", x)
+    squeeze = x.dim() == 2
+    if squeeze:
+        x = x.unsqueeze(0)
+    if x.dim() != 3:
+        raise ValueError(f"input must be (B,V,in) or (V,in), got {tuple(x.shape)}")
+    if weight.dim() == 3:  # Batch_Image_ZERON_GCNGCN.weight1 is (1,in,out)
+        weight = weight[0]
+    csr = adj if isinstance(adj, CsrAdjacency) else csr_from_dense(adj)
+    if csr.V != x.shape[1]:
+        raise ValueError(f"adjacency is {csr.V}x{csr.V} but input has {x.shape[1]} vertices")
+    if weight.shape[0] != x.shape[2]:
+        raise ValueError(f"weight is {tuple(weight.shape)} but input has {x.shape[2]} features")
+    fuse_relu = activation is F.relu or activation is torch.relu
+    y = ZeroNGCNFunction.apply(x, weight, bias, csr, weight.shape[1] // split, fuse_relu)
+    if squeeze:
+        y = y.squeeze(0)
+    if activation is None or fuse_relu:
+        return y
+    return activation(y)
+
+
+class ZERON_GCN(nn.Module):
+    """layers.py:14-41: un-batched encoder layer, weight (in,out), split out//10."""
+
+    split = 10
+
+    def __init__(self, in_features, out_features, bias=True):
+        super().__init__()
+        self.in_features = in_features
+        self.out_features = out_features
+        self.weight = Parameter(torch.Tensor(in_features, out_features))
+        if bias:
+            self.bias = Parameter(torch.Tensor(out_features))
+        else:
+            self.register_parameter("bias", None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        stdv = 6. / math.sqrt(self.weight.size(1) + self.weight.size(0))
+        self.weight.data.uniform_(-stdv, stdv)
+        if self.bias is not None:
+            self.bias.data.uniform_(-0, 0)
+
+    def forward(self, input, adj, activation):
+        return zeron_gcn(input, self.weight, self.bias, adj, self.split, activation)
+
+
+class BatchZERON_GCN(ZERON_GCN):
+    """layers.py:123-152: batched encoder layer (same parameters, input (B,V,in))."""
+
+
+class Batch_Image_ZERON_GCNGCN(nn.Module):
+    """layers.py:84-116: deformation-block layer, weight1 (1,in,out), split out//3."""
+
+    split = 3
+
+    def __init__(self, in_features, out_features, bias=True):
+        super().__init__()
+        self.in_features = in_features
+        self.out_features = out_features
+        self.weight1 = Parameter(torch.Tensor(1, in_features, out_features))
+        if bias:
+            self.bias = Parameter(torch.Tensor(out_features))
+        else:
+            self.register_parameter("bias", None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        stdv = 6. / math.sqrt((self.weight1.size(1) + self.weight1.size(0)))
+        stdv *= .3
+        self.weight1.data.uniform_(-stdv, stdv)
+        if self.bias is not None:
+            self.bias.data.uniform_(-.1, .1)
+
+    def forward(self, input, adj, activation):
+        return zeron_gcn(input, self.weight1, self.bias, adj, self.split, activation)
+
+
+class GCNMax(nn.Module):
+    """layers.py:43-79: encoder head; max over vertices of the ACTIVATED layer output (:76-78)."""
+
+    pool_activated = True
+
+    def __init__(self, in_features, print_length):
+        super().__init__()
+        self.in_features = in_features
+        self.print_length = print_length
+        self.weight_Ws = nn.ParameterList(Parameter(torch.Tensor(in_features, print_length)) for i in range(1))
+        self.weight_Bs = nn.ParameterList(Parameter(torch.Tensor(print_length)) for i in range(1))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        for i in range(1):
+            stdv = 6. / math.sqrt(self.weight_Bs[i].size(0))
+            self.weight_Bs[i].data.uniform_(-stdv, stdv)
+            stdv = 6. / math.sqrt(self.weight_Ws[i].size(0) + self.weight_Ws[i].size(1))
+            self.weight_Ws[i].data.uniform_(-stdv, stdv)
+
+    def forward(self, r_s, adj, activation):
+        v_s = zeron_gcn(r_s, self.weight_Ws[0], self.weight_Bs[0], adj, 10, None)
+        pooled = activation(v_s) if self.pool_activated else v_s
+        return torch.max(pooled, dim=-2)[0]
+
+
+class BatchGCNMax(GCNMax):
+    """layers.py:157-189: batched head; pools the PRE-activation tensor (:186-187), unlike GCNMax."""
+
+    pool_activated = False
+
+
+ZeroNGCN = ZERON_GCN  # the name BASELINE.json's north_star uses
+
+
+class Image_ZERON_GCNGCN(nn.Module):
+    """old_GEOMetrics/layers.py:106-141: the un-batched deformation-block layer that
+    ``MeshDeformationBlock`` (models.py:138-201) instantiates; weight1 (in,out), split out//3.  The
+    legacy caller passes the adjacency dict and the layer reads ``adj['adj']``; both forms work."""
+
+    split = 3
+
+    def __init__(self, in_features, out_features, bias=True):
+        super().__init__()
+        self.in_features = in_features
+        self.out_features = out_features
+        self.weight1 = Parameter(torch.Tensor(in_features, out_features))
+        if bias:
+            self.bias = Parameter(torch.Tensor(out_features))
+        else:
+            self.register_parameter("bias", None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        stdv = 6. / math.sqrt((self.weight1.size(1) + self.weight1.size(0)))
+        stdv *= .6
+        self.weight1.data.uniform_(-stdv, stdv)
+        if self.bias is not None:
+            self.bias.data.uniform_(-.1, .1)
+
+    def forward(self, input, adj, activation):
+        if isinstance(adj, dict):
+            adj = adj["adj"]
+        return zeron_gcn(input, self.weight1, self.bias, adj, self.split, activation)

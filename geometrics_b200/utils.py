@@ -1,0 +1,323 @@
+"""Host-side mirror of the hot-path functions of the reference's ``utils.py``: same names, argument
+meaning and return values, with the chains of small torch kernels replaced by calls into
+``libgeom_b200.so`` (sm_100a).  Everything here is CUDA-only; there is no CPU fallback.
+
+Reference map:
+  batch_sample              utils.py:590-633
+  batch_point_to_point      utils.py:393-438
+  batch_point_to_surface    utils.py:441-502  (+ calc_point_to_line :506-550, edge :553-570, Plane :572-587)
+  calc_adj / normalize_adj / adj_init   utils.py:96-131
+  chamfer_dist / tri_dist   module singletons, utils.py:31-35
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .chamfer_distance import ChamferDistance, chamfer_forward
+from .tri_distance import TriDistance, tri_forward
+
+chamfer_dist = ChamferDistance()  # utils.py:32
+tri_dist = TriDistance()          # utils.py:35
+
+
+# ------------------------------------------------------------------------------------------------
+# adjacency (one-time setup; plain torch, device-agnostic)
+# ------------------------------------------------------------------------------------------------
+def calc_adj(faces: torch.Tensor) -> torch.Tensor:
+    """Dense binary adjacency with self loops (utils.py:113-131)."""
+    v1, v2, v3 = faces[:, 0], faces[:, 1], faces[:, 2]
+    num_verts = int(faces.max())
+    adj = torch.eye(num_verts + 1, device=faces.device)
+    adj[(v1, v2)] = 1
+    adj[(v1, v3)] = 1
+    adj[(v2, v1)] = 1
+    adj[(v2, v3)] = 1
+    adj[(v3, v1)] = 1
+    adj[(v3, v2)] = 1
+    return adj
+
+
+def normalize_adj(mx: torch.Tensor) -> torch.Tensor:
+    """Row-normalise (utils.py:96-101): adj[i, j] = (1 / rowsum_i) * mx[i, j]."""
+    r_inv = (1.0 / mx.sum(1)).view(-1)
+    r_inv[r_inv != r_inv] = 0.0
+    return r_inv.unsqueeze(1) * mx
+
+
+def adj_init(faces: torch.Tensor) -> dict:
+    """utils.py:104-112: {'adj': row-normalised, 'adj_orig': binary, 'faces': faces}."""
+    adj = calc_adj(faces)
+    return {"adj": normalize_adj(adj), "adj_orig": adj.clone(), "faces": faces}
+
+
+# ------------------------------------------------------------------------------------------------
+# face sampler
+# ------------------------------------------------------------------------------------------------
+def _faces_i64(faces: torch.Tensor, dev) -> torch.Tensor:
+    if faces.dim() != 2 or faces.shape[1] != 3:
+        raise ValueError(f"faces must have shape (F, 3), got {tuple(faces.shape)}")
+    if faces.dtype != torch.int64 or faces.device != dev or not faces.is_contiguous():
+        faces = faces.to(device=dev, dtype=torch.int64).contiguous()
+    return faces
+
+
+def face_areas(verts: torch.Tensor, faces: torch.Tensor, normalise: bool = True) -> torch.Tensor:
+    """(B,F) face areas of every mesh (utils.py:596-601), divided by the per-mesh total when
+    ``normalise`` (utils.py:602).  No gradient, as in the reference (areas only feed multinomial)."""
+    _lib.require_cuda_f32("verts", verts, 3)
+    L = _lib.lib()
+    verts = verts.detach().contiguous()
+    faces = _faces_i64(faces, verts.device)
+    b, v, _ = verts.shape
+    f = faces.shape[0]
+    with torch.cuda.device(verts.device):
+        areas = torch.empty((b, f), dtype=torch.float32, device=verts.device)
+        _lib.check(L.geom_face_areas(b, v, verts.data_ptr(), f, faces.data_ptr(), areas.data_ptr(),
+                                     1 if normalise else 0, _lib.current_stream_ptr(verts.device)), "geom_face_areas")
+    return areas
+
+
+class SampleFunction(torch.autograd.Function):
+    """points = barycentric combination of the chosen faces' vertices; gradient to ``verts`` only
+    (utils.py:614-631: the three index_selects are the only differentiable path)."""
+
+    @staticmethod
+    def forward(ctx, verts, faces, choices, r1, r2):
+        L = _lib.lib()
+        vc = verts.detach().contiguous()
+        b, v, _ = vc.shape
+        num = choices.numel() // max(b, 1)
+        dev = vc.device
+        with torch.cuda.device(dev):
+            points = torch.empty((b, num, 3), dtype=torch.float32, device=dev)
+            _lib.check(L.geom_sample_fwd(b, v, vc.data_ptr(), faces.shape[0], faces.data_ptr(), num,
+                                         choices.data_ptr(), r1.data_ptr(), r2.data_ptr(), points.data_ptr(),
+                                         _lib.current_stream_ptr(dev)), "geom_sample_fwd")
+        ctx.save_for_backward(faces, choices, r1, r2)
+        ctx.shape = (b, v, num)
+        return points
+
+    @staticmethod
+    def backward(ctx, grad_points):
+        faces, choices, r1, r2 = ctx.saved_tensors
+        b, v, num = ctx.shape
+        L = _lib.lib()
+        g = grad_points.contiguous()
+        dev = g.device
+        with torch.cuda.device(dev):
+            gv = torch.empty((b, v, 3), dtype=torch.float32, device=dev)
+            _lib.check(L.geom_sample_bwd(b, v, faces.shape[0], faces.data_ptr(), num, choices.data_ptr(),
+                                         r1.data_ptr(), r2.data_ptr(), g.data_ptr(), gv.data_ptr(),
+                                         _lib.current_stream_ptr(dev)), "geom_sample_bwd")
+        return gv, None, None, None, None
+
+
+def batch_sample(verts: torch.Tensor, faces: torch.Tensor, num: int = 10000, *, choices=None, r1=None, r2=None,
+                 reference_rng: bool = False, generator=None) -> torch.Tensor:
+    """Area-weighted uniform surface samples (B,num,3), differentiable w.r.t. ``verts``
+    (utils.py:590-633).
+
+    Random draws: one batched ``torch.multinomial`` over the normalised areas, then two uniform
+    vectors of B*num, in that order.  ``reference_rng=True`` instead issues the per-mesh multinomial
+    calls in the reference's order (utils.py:606-612) so that the same CUDA seed gives the same
+    draws.  ``choices`` (B*num int64 face ids), ``r1`` and ``r2`` (B*num uniforms; u = sqrt(r1),
+    v = r2) can be supplied to make the result a pure function of its inputs (parity tests)."""
+    _lib.require_cuda_f32("verts", verts, 3)
+    dev = verts.device
+    faces = _faces_i64(faces, dev)
+    b = verts.shape[0]
+    if choices is None:
+        areas = face_areas(verts, faces)
+        if reference_rng:
+            choices = torch.cat([torch.multinomial(a, num, True, generator=generator) for a in areas])
+        else:
+            choices = torch.multinomial(areas, num, True, generator=generator).view(-1)
+    choices = choices.to(device=dev, dtype=torch.int64).contiguous().view(-1)
+    if r1 is None:
+        r1 = torch.rand(b * num, 1, device=dev, generator=generator)  # dist_uni.sample_n, utils.py:627
+    if r2 is None:
+        r2 = torch.rand(b * num, 1, device=dev, generator=generator)  # utils.py:628
+    r1 = r1.to(device=dev, dtype=torch.float32).contiguous().view(-1)
+    r2 = r2.to(device=dev, dtype=torch.float32).contiguous().view(-1)
+    if choices.numel() != b * num or r1.numel() != b * num or r2.numel() != b * num:
+        raise ValueError("choices / r1 / r2 must hold B*num entries")
+    return SampleFunction.apply(verts, faces, choices, r1, r2)
+
+
+# ------------------------------------------------------------------------------------------------
+# Chamfer loss
+# ------------------------------------------------------------------------------------------------
+class _AllReduceSum(torch.autograd.Function):
+    """Sum partial loss sums over the ranks of ``group``; every rank keeps the same upstream gradient."""
+
+    @staticmethod
+    def forward(ctx, sums, group):
+        import torch.distributed as dist
+
+        out = sums.clone()
+        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        return grad, None
+
+
+def all_reduce_sums(sums: torch.Tensor, group=None) -> torch.Tensor:
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return sums
+    return _AllReduceSum.apply(sums, group)
+
+
+def world_size(group=None) -> int:
+    import torch.distributed as dist
+
+    return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+
+class ChamferLossFunction(torch.autograd.Function):
+    """(xyz1, xyz2, idx1, idx2) -> sums (2,): sums[0] = sum |xyz2[idx1] - xyz1|^2 over xyz1's rows,
+    sums[1] = sum |xyz1[idx2] - xyz2|^2 over xyz2's rows.  Gradient to both point sets with the
+    indices held constant (what autograd gives for utils.py:413-417)."""
+
+    @staticmethod
+    def forward(ctx, xyz1, xyz2, idx1, idx2):
+        L = _lib.lib()
+        a, c = xyz1.detach().contiguous(), xyz2.detach().contiguous()
+        b, n, _ = a.shape
+        m = c.shape[1]
+        dev = a.device
+        with torch.cuda.device(dev):
+            sums = torch.empty(2, dtype=torch.float32, device=dev)
+            wsb = L.geom_chamfer_loss_workspace_bytes(b, n, m)
+            ws = torch.empty(max(wsb // 16, 1) * 2, dtype=torch.float64, device=dev)
+            _lib.check(L.geom_chamfer_loss_fwd(b, n, a.data_ptr(), m, c.data_ptr(), idx1.data_ptr(), idx2.data_ptr(),
+                                               None, None, sums.data_ptr(), ws.data_ptr(), ws.numel() * 8,
+                                               _lib.current_stream_ptr(dev)), "geom_chamfer_loss_fwd")
+        ctx.save_for_backward(a, c, idx1, idx2)
+        return sums
+
+    @staticmethod
+    def backward(ctx, grad_sums):
+        a, c, idx1, idx2 = ctx.saved_tensors
+        L = _lib.lib()
+        b, n, _ = a.shape
+        m = c.shape[1]
+        dev = a.device
+        w = grad_sums.to(torch.float32).contiguous()
+        need1, need2 = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        with torch.cuda.device(dev):
+            g1 = torch.empty_like(a) if need1 else None
+            g2 = torch.empty_like(c) if need2 else None
+            _lib.check(L.geom_chamfer_loss_bwd(b, n, a.data_ptr(), m, c.data_ptr(), idx1.data_ptr(), idx2.data_ptr(),
+                                               w.data_ptr(), g1.data_ptr() if need1 else None,
+                                               g2.data_ptr() if need2 else None, _lib.current_stream_ptr(dev)),
+                       "geom_chamfer_loss_bwd")
+        return g1, g2, None, None
+
+
+def chamfer_loss_sums(xyz1: torch.Tensor, xyz2: torch.Tensor):
+    """NN search + loss sums: -> (sums (2,) differentiable, idx1 (B,n), idx2 (B,m))."""
+    _, idx1, _, idx2 = chamfer_forward(xyz1, xyz2, want_dist=False)
+    return ChamferLossFunction.apply(xyz1, xyz2, idx1, idx2), idx1, idx2
+
+
+def _f_score(gt_points, pred_points, idx_p, idx_g, num):
+    """F1 at 1e-2 on 0.57-scaled coordinates (utils.py:424-436), without the per-item Python loop."""
+    b = gt_points.shape[0]
+    pred_counters = torch.gather(pred_points, 1, idx_p.long().unsqueeze(-1).expand(-1, -1, 3))
+    gt_counters = torch.gather(gt_points, 1, idx_g.long().unsqueeze(-1).expand(-1, -1, 3))
+    dist_to_pred = torch.sqrt(torch.sum((.57 * pred_counters - .57 * gt_points) ** 2, dim=-1))
+    dist_to_gt = torch.sqrt(torch.sum((.57 * gt_counters - .57 * pred_points) ** 2, dim=-1))
+    recall = (dist_to_pred <= 1e-2).sum(1).double() / float(num)
+    precision = (dist_to_gt <= 1e-2).sum(1).double() / float(num)
+    return float((2 * (precision * recall) / (precision + recall + 1e-8)).sum() / b)
+
+
+def batch_point_to_point(pred_vert, adj_info, gt_points, num=1000, f1=False, group=None):
+    """Chamfer loss between ``num`` surface samples of the predicted meshes and the ground-truth
+    points (utils.py:393-438): ``(dist_1 + dist_2) * 3000`` [, f_score].  With ``group`` the batch is
+    taken to be sharded over that process group and the means are global (one all-reduce of two
+    scalars)."""
+    pred_points = batch_sample(pred_vert, adj_info["faces"], num=num)
+    gt = gt_points.contiguous()
+    sums, id_p, id_g = chamfer_loss_sums(gt, pred_points)
+    sums = all_reduce_sums(sums, group)
+    ws = world_size(group)
+    dist_2 = sums[0] / float(gt.shape[0] * gt.shape[1] * ws)                    # utils.py:417
+    dist_1 = sums[1] / float(pred_points.shape[0] * pred_points.shape[1] * ws)  # utils.py:416
+    loss = (dist_1 + dist_2) * 3000
+    if f1:
+        return loss, _f_score(gt, pred_points.detach(), id_p, id_g, num)
+    return loss
+
+
+# ------------------------------------------------------------------------------------------------
+# point-to-surface loss
+# ------------------------------------------------------------------------------------------------
+class TriLossFunction(torch.autograd.Function):
+    """sum over all ground-truth points of |closest point on the winning triangle - p|^2, with the
+    closest point recomputed differentiably from the region option (utils.py:472-481, 506-550)."""
+
+    @staticmethod
+    def forward(ctx, gt_points, verts, faces, option, index):
+        L = _lib.lib()
+        p, v = gt_points.detach().contiguous(), verts.detach().contiguous()
+        b, n, _ = p.shape
+        dev = p.device
+        with torch.cuda.device(dev):
+            total = torch.empty(1, dtype=torch.float32, device=dev)
+            wsb = L.geom_tri_loss_workspace_bytes(b, n)
+            ws = torch.empty(max(wsb // 8, 1), dtype=torch.float64, device=dev)
+            _lib.check(L.geom_tri_loss_fwd(b, n, p.data_ptr(), v.shape[1], v.data_ptr(), faces.shape[0],
+                                           faces.data_ptr(), option.data_ptr(), index.data_ptr(), None, None,
+                                           total.data_ptr(), ws.data_ptr(), ws.numel() * 8,
+                                           _lib.current_stream_ptr(dev)), "geom_tri_loss_fwd")
+        ctx.save_for_backward(p, v, faces, option, index)
+        return total
+
+    @staticmethod
+    def backward(ctx, grad_total):
+        p, v, faces, option, index = ctx.saved_tensors
+        L = _lib.lib()
+        b, n, _ = p.shape
+        dev = p.device
+        w = grad_total.to(torch.float32).contiguous()
+        with torch.cuda.device(dev):
+            gv = torch.empty_like(v)
+            _lib.check(L.geom_tri_loss_bwd(b, n, p.data_ptr(), v.shape[1], v.data_ptr(), faces.shape[0],
+                                           faces.data_ptr(), option.data_ptr(), index.data_ptr(), w.data_ptr(),
+                                           gv.data_ptr(), _lib.current_stream_ptr(dev)), "geom_tri_loss_bwd")
+        return None, gv, None, None, None
+
+
+def point_to_surface_sum(gt_points, pred_vert, faces):
+    """TriDistance search + differentiable closest-point sum -> (sum (1,), option, index)."""
+    _lib.require_cuda_f32("pred_vert", pred_vert, 3)
+    faces = _faces_i64(faces, pred_vert.device)
+    with torch.no_grad():  # the search consumes positions only (its outputs carry no gradient)
+        tri1, tri2, tri3 = (torch.index_select(pred_vert, 1, faces[:, k]) for k in range(3))  # utils.py:467-469
+        _, option, index = tri_forward(gt_points, tri1, tri2, tri3)
+    gt = gt_points.contiguous()
+    return TriLossFunction.apply(gt, pred_vert, faces, option, index), option, index
+
+
+def batch_point_to_surface(pred_vert, adj_info, gt_points, num=1000, f1=False, group=None):
+    """Training loss (utils.py:441-502): Chamfer term from the surface samples to the ground truth
+    plus point-to-surface term from the ground truth to the predicted triangles,
+    ``(dist_1 + dist_2) * 3000`` [, f_score]."""
+    pred_points = batch_sample(pred_vert, adj_info["faces"], num=num)
+    gt = gt_points.contiguous()
+    sums, id_p, id_g = chamfer_loss_sums(gt, pred_points)
+    tri_sum, _, _ = point_to_surface_sum(gt, pred_vert, adj_info["faces"])
+    part = all_reduce_sums(torch.cat((sums[1:2], tri_sum)), group)
+    ws = world_size(group)
+    dist_1 = part[0] / float(pred_points.shape[0] * pred_points.shape[1] * ws)  # utils.py:462
+    dist_2 = part[1] / float(gt.shape[0] * gt.shape[1] * ws)                    # utils.py:481, 549
+    loss = (dist_1 + dist_2) * 3000
+    if f1:
+        return loss, _f_score(gt, pred_points.detach(), id_p, id_g, num)
+    return loss

@@ -121,6 +121,76 @@ GEOM_API int geom_tri_fwd(int b, int n, const float *xyz, int m, const float *tr
                  const float *tri3, float *dist, int *point, int *index,
                  unsigned flags, geom_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Point-to-surface loss on the search result (forward sum, backward scatter to the vertices).
+ * Replaces batch_point_to_surface's gathers (utils.py:467-479) + calc_point_to_line
+ * (utils.py:506-550) + classes edge / Plane (utils.py:553-587) and their autograd backward.
+ * xyz (B,n,3) ground-truth points; verts (B,V,3) predicted vertices; faces (F,3) int64 shared by the
+ * batch (adj_info['faces']); option / index (B,n) int32 from geom_tri_fwd.
+ *   sum[0] = sum over all B*n points of |c - p|^2, c = the closest point the option selects
+ * (vertex / edge projection / plane projection; the CA edge uses its own direction as the Python
+ * does).  dist (B,n) and closest (B,n,3) are optional outputs (NULL to skip).
+ * Backward: grad_verts (B,V,3) = d(weight[0] * sum)/dverts; weight = 1 float in DEVICE memory.
+ * ------------------------------------------------------------------------------------------- */
+GEOM_API size_t geom_tri_loss_workspace_bytes(int b, int n);
+GEOM_API int geom_tri_loss_fwd(int b, int n, const float *xyz, int V, const float *verts, int F,
+                      const int64_t *faces, const int *option, const int *index, float *dist,
+                      float *closest, float *sum, void *workspace, size_t workspace_bytes,
+                      geom_stream_t stream);
+GEOM_API int geom_tri_loss_bwd(int b, int n, const float *xyz, int V, const float *verts, int F,
+                      const int64_t *faces, const int *option, const int *index, const float *weight,
+                      float *grad_verts, geom_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Differentiable face sampler.
+ * Replaces batch_sample (utils.py:590-633) except its random draws, which stay with the caller's
+ * generator (torch.multinomial over the areas, two uniform vectors).
+ * geom_face_areas: areas (B,F) = 0.5*|cross(v0-v1, v1-v2)| per face (utils.py:596-601), divided by
+ *   the per-mesh sum when normalise != 0 (utils.py:602).
+ * geom_sample_fwd: points[b,s] = (1-u) v0 + u(1-v) v1 + u v v2 with (v0,v1,v2) the vertices of face
+ *   choices[b*num+s] of mesh b, u = sqrt(r1), v = r2 (utils.py:614-631); bit-identical to the torch
+ *   expression for identical (choices, r1, r2).
+ * geom_sample_bwd: grad_verts (B,V,3) = scatter-add of the barycentric-weighted grad_points (the
+ *   index_add autograd runs for utils.py:624-626); grad_verts is overwritten.
+ * ------------------------------------------------------------------------------------------- */
+GEOM_API int geom_face_areas(int b, int V, const float *verts, int F, const int64_t *faces, float *areas,
+                    int normalise, geom_stream_t stream);
+GEOM_API int geom_sample_fwd(int b, int V, const float *verts, int F, const int64_t *faces, int num,
+                    const int64_t *choices, const float *r1, const float *r2, float *points,
+                    geom_stream_t stream);
+GEOM_API int geom_sample_bwd(int b, int V, int F, const int64_t *faces, int num, const int64_t *choices,
+                    const float *r1, const float *r2, const float *grad_points, float *grad_verts,
+                    geom_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * 0N-GCN layer.
+ * Replaces the forward of ZERON_GCN (layers.py:34-41), Batch_Image_ZERON_GCNGCN (layers.py:107-116),
+ * BatchZERON_GCN (layers.py:143-152) and the linear part of GCNMax / BatchGCNMax (layers.py:61-72,
+ * 176-185):   support = X W ;  Y = [ adj . support[:, :ksplit] | support[:, ksplit:] ] + bias
+ * with ksplit = out//3 or out//10 chosen by the caller.  The reference multiplies by a dense (V,V)
+ * adjacency; here it is CSR, built once from that dense matrix:
+ *   geom_csr_count(V, adj, transpose, row_cnt, row_ptr): row_ptr[0..V] (exclusive scan of the per-row
+ *     non-zero counts; row_cnt is a V-int scratch).  The caller reads row_ptr[V] = nnz, allocates
+ *     col_idx / val, and calls geom_csr_fill.  transpose != 0 builds the CSR of adj^T (backward).
+ * geom_zeron_gcn_fwd: X (B,V,in), W (in,out), bias (out) or NULL, Y (B,V,out); relu != 0 fuses
+ *   max(.,0); workspace >= geom_zeron_gcn_workspace_bytes(B,V,ksplit), 16-byte aligned.
+ * geom_zeron_gcn_bwd_smooth: dS (B,V,out) = [ adj^T . dY[:, :ksplit] | dY[:, ksplit:] ] from the CSR
+ *   of adj^T; the caller finishes with the two plain GEMMs dX = dS W^T, dW = X^T dS.
+ * fp32 throughout (fp32 accumulate); differs from the dense reference only by summation order.
+ * ------------------------------------------------------------------------------------------- */
+GEOM_API int geom_csr_count(int V, const float *adj, int transpose, int *row_cnt, int *row_ptr,
+                   geom_stream_t stream);
+GEOM_API int geom_csr_fill(int V, const float *adj, int transpose, const int *row_ptr, int *col_idx,
+                  float *val, geom_stream_t stream);
+GEOM_API size_t geom_zeron_gcn_workspace_bytes(int b, int V, int ksplit);
+GEOM_API int geom_zeron_gcn_fwd(int b, int V, int in_features, int out_features, int ksplit, const float *X,
+                       const float *W, const float *bias, const int *row_ptr, const int *col_idx,
+                       const float *val, float *Y, int relu, void *workspace, size_t workspace_bytes,
+                       geom_stream_t stream);
+GEOM_API int geom_zeron_gcn_bwd_smooth(int b, int V, int out_features, int ksplit, const int *t_row_ptr,
+                              const int *t_col_idx, const float *t_val, const float *dY, float *dS,
+                              geom_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
