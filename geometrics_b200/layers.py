@@ -132,6 +132,11 @@ def zeron_gcn(x, weight, bias, adj, split: int, activation=None):
     csr = adj if isinstance(adj, CsrAdjacency) else csr_from_dense(adj)
     if csr.V != x.shape[1]:
         raise ValueError(f"adjacency is {csr.V}x{csr.V} but input has {x.shape[1]} vertices")
+    for name, t in (("weight", weight), ("bias", bias)):
+        if t is not None and (t.device != x.device or t.dtype != torch.float32):
+            raise RuntimeError(f"{name} must be float32 on {x.device}, got {t.dtype} on {t.device}")
+    if isinstance(adj, torch.Tensor) and adj.device != x.device:
+        raise RuntimeError(f"adj on {adj.device} but input on {x.device}")
     if weight.shape[0] != x.shape[2]:
         raise ValueError(f"weight is {tuple(weight.shape)} but input has {x.shape[2]} features")
     fuse_relu = activation is F.relu or activation is torch.relu

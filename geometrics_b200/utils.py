@@ -165,9 +165,11 @@ class _AllReduceSum(torch.autograd.Function):
 
 
 def all_reduce_sums(sums: torch.Tensor, group=None) -> torch.Tensor:
+    """Sum over the ranks of ``group``.  ``group=None`` means "not sharded": no communication (pass
+    ``torch.distributed.group.WORLD`` explicitly to reduce over the default group)."""
     import torch.distributed as dist
 
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+    if group is None or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return sums
     return _AllReduceSum.apply(sums, group)
 
@@ -175,7 +177,9 @@ def all_reduce_sums(sums: torch.Tensor, group=None) -> torch.Tensor:
 def world_size(group=None) -> int:
     import torch.distributed as dist
 
-    return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    if group is None or not (dist.is_available() and dist.is_initialized()):
+        return 1
+    return dist.get_world_size(group)
 
 
 class ChamferLossFunction(torch.autograd.Function):

@@ -38,11 +38,11 @@ def setup(cuda):
     return mods, adj.to(cuda), pos.to(cuda), pooled.to(cuda), x120.to(cuda)
 
 
-def test_weights_match_golden_run(gold, setup):
-    mods = setup[0]
-    for k, m in mods.items():
-        assert abs(G.checksum(m.cpu()) - float(gold["wsum_" + k])) <= 1e-6 * float(gold["wsum_" + k]), k
-        m.to("cuda")
+def test_weights_match_golden_run(gold):
+    import geometrics_b200 as g
+
+    for k, m in G.build(g).items():  # fresh CPU modules: same constructor order + seeds as the golden run
+        assert abs(G.checksum(m) - float(gold["wsum_" + k])) <= 1e-6 * float(gold["wsum_" + k]), k
 
 
 def test_csr_matches_dense(cuda):
