@@ -32,7 +32,8 @@ SYMBOLS = {
     "geom_chamfer_loss_workspace_bytes": (_sz, [_i, _i, _i]),
     "geom_chamfer_loss_fwd": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "geom_chamfer_loss_bwd": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "geom_tri_fwd": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _u, _vp]),
+    "geom_tri_workspace_bytes": (_sz, [_i, _i]),
+    "geom_tri_fwd": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _u, _vp]),
     "geom_tri_loss_workspace_bytes": (_sz, [_i, _i]),
     "geom_tri_loss_fwd": (_i, [_i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "geom_tri_loss_bwd": (_i, [_i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -7,25 +7,35 @@
 // face index wins.
 //
 // Design (not a translation):
-//   * Everything that depends only on the triangle (edge vectors, squared edge lengths, the face
-//     normal, the three in-plane edge normals cross(N, edge) used by is_above, and the unit normal
-//     used by the plane projection) is computed ONCE per triangle when a tile is staged into shared
-//     memory, not once per (point, triangle) pair as the reference does (tri_distance.cu:140-148).
-//     The per-pair work shrinks to 9 subtractions, 3 dot products, 3 IEEE divisions and the region
-//     logic.  Each value is produced by the same rounding sequence the reference binary uses
-//     (explicit _rn intrinsics; see DESIGN.md "TriDistance arithmetic").
-//   * Each thread carries PR points so one broadcast LDS.128 of a triangle record feeds PR
-//     evaluations.
+//   * Everything that depends only on the triangle (edge vectors, squared edge lengths and their
+//     correctly rounded reciprocals, the face normal, the three in-plane edge normals cross(N, edge)
+//     used by is_above, the unit normal of the plane projection) is computed ONCE per triangle when
+//     a warp stages 32 triangles into its shared-memory slab, not once per (point, triangle) pair as
+//     the reference does (tri_distance.cu:140-148).  Each value is produced by the same rounding
+//     sequence the reference binary uses (explicit _rn intrinsics; DESIGN.md "TriDistance").
+//   * The three IEEE divisions per pair become  q = a*y; r = fma(-b,q,a); q = fma(r,y,q)  (twice)
+//     with y = rn(1/b) precomputed per triangle: Markstein's correction, correctly rounded whenever
+//     no intermediate can under/overflow; operands outside that comfortable range take __fdiv_rn.
+//   * The inner loop is branch-free (the reference's if/else region cascade becomes predicate logic
+//     and selects; a warp holds 32 different points, so the cascade diverged on every triangle) and
+//     tracks only (best distance, face index).  The region option of the winner is recomputed in the
+//     epilogue by the exact cascade.
+//   * Every warp is an independent worker; work units (32*PR points) x (chunk of a 512-triangle
+//     reference tile) are pulled from a global ticket, so small batches still fill the GPU and there
+//     is no wave quantisation.  Chunks meet in 64-bit keys (distance bits << 32 | face index) merged by
+//     filtered atomicMin = "strictly smaller wins, lowest index on ties", the reference's rule.
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace geom {
 namespace tri {
 
-constexpr int kThreads = 128;
-constexpr int kPR = 2;                  // points per thread
-constexpr int kSubTile = 256;           // triangles staged per shared-memory tile
-constexpr int kRecVec = 10;             // float4 per triangle record
-constexpr int kRefTile = 512;           // reference tile (tri_distance.cu:106)
+constexpr int kWarps = 4;
+constexpr int kThreads = 32 * kWarps;
+constexpr int kRecVec = 10;    // float4 per triangle record
+constexpr int kRefTile = 512;  // reference tile (tri_distance.cu:106)
 
 struct V3 {
     float x, y, z;
@@ -55,33 +65,45 @@ __device__ __forceinline__ V3 cross_s2(V3 X, V3 Y)
               __fmaf_rn(X.x, Y.y, -__fmul_rn(X.y, Y.x)));
 }
 __device__ __forceinline__ bool in_range(float a) { return (a <= 1.0f) && (a >= 0.0f); }
+__device__ __forceinline__ V3 xyz(float4 v) { return v3(v.x, v.y, v.z); }
+__device__ __forceinline__ V3 sel3(bool c, V3 a, V3 b) { return v3(c ? a.x : b.x, c ? a.y : b.y, c ? a.z : b.z); }
+__device__ __forceinline__ V3 fma3(V3 d, float t, V3 s)
+{
+    return v3(__fmaf_rn(d.x, t, s.x), __fmaf_rn(d.y, t, s.y), __fmaf_rn(d.z, t, s.z));
+}
+
+// Operand range in which Markstein's correction is exact: every intermediate stays a normal number.
+constexpr float kDivLo = 1.0842021724855044e-19f;  // 2^-63
+constexpr float kDivHi = 9.2233720368547758e+18f;  // 2^63
+__device__ __forceinline__ bool div_safe_den(float b) { return b >= kDivLo && b <= kDivHi; }
 
 // Triangle record, 10 x float4:
-//  0: A.xyz | |AB|^2     1: B.xyz | |BC|^2     2: C.xyz | |CA|^2
-//  3: AB.xyz             4: BC.xyz             5: CA.xyz
-//  6: cross(N,AB)        7: cross(N,BC)        8: cross(N,CA)        9: N / |N|
+//  0: A.xyz | |AB|^2          1: B.xyz | |BC|^2          2: C.xyz | |CA|^2
+//  3: AB.xyz | rn(1/|AB|^2)   4: BC.xyz | rn(1/|BC|^2)   5: CA.xyz | rn(1/|CA|^2)
+//  6: cross(N,AB) | fast-division flag   7: cross(N,BC)   8: cross(N,CA)   9: N / |N|
 __device__ __forceinline__ void build_record(float4 *rec, V3 A, V3 B, V3 C)
 {
     const V3 AB = vsub(B, A), BC = vsub(C, B), CA = vsub(A, C);
     const V3 N = cross_s2(vsub(A, B), CA);  // cross(A-B, A-C), tri_distance.cu:148
     const V3 xab = cross_s2(N, AB), xbc = cross_s2(N, BC), xca = cross_s2(N, CA);
     const float inv = __frcp_rn(__fsqrt_rn(dot_s1(N, N)));  // normalize(), tri_distance.cu:77-81
-    rec[0] = make_float4(A.x, A.y, A.z, dot_s1(AB, AB));
-    rec[1] = make_float4(B.x, B.y, B.z, dot_s1(BC, BC));
-    rec[2] = make_float4(C.x, C.y, C.z, dot_s1(CA, CA));
-    rec[3] = make_float4(AB.x, AB.y, AB.z, 0.f);
-    rec[4] = make_float4(BC.x, BC.y, BC.z, 0.f);
-    rec[5] = make_float4(CA.x, CA.y, CA.z, 0.f);
-    rec[6] = make_float4(xab.x, xab.y, xab.z, 0.f);
+    const float lab = dot_s1(AB, AB), lbc = dot_s1(BC, BC), lca = dot_s1(CA, CA);
+    const bool safe = div_safe_den(lab) && div_safe_den(lbc) && div_safe_den(lca);
+    rec[0] = make_float4(A.x, A.y, A.z, lab);
+    rec[1] = make_float4(B.x, B.y, B.z, lbc);
+    rec[2] = make_float4(C.x, C.y, C.z, lca);
+    rec[3] = make_float4(AB.x, AB.y, AB.z, __frcp_rn(lab));
+    rec[4] = make_float4(BC.x, BC.y, BC.z, __frcp_rn(lbc));
+    rec[5] = make_float4(CA.x, CA.y, CA.z, __frcp_rn(lca));
+    rec[6] = make_float4(xab.x, xab.y, xab.z, safe ? 1.0f : 0.0f);
     rec[7] = make_float4(xbc.x, xbc.y, xbc.z, 0.f);
     rec[8] = make_float4(xca.x, xca.y, xca.z, 0.f);
     rec[9] = make_float4(__fmul_rn(N.x, inv), __fmul_rn(N.y, inv), __fmul_rn(N.z, inv), 0.f);
 }
 
-__device__ __forceinline__ V3 xyz(float4 v) { return v3(v.x, v.y, v.z); }
-
-// One (point, triangle) evaluation, tri_distance.cu:150-191.
-__device__ __forceinline__ float tri_pair(V3 p, const float4 *__restrict__ rec, float &option)
+// One (point, triangle) evaluation with the reference's cascade, tri_distance.cu:150-191.
+// Used by the epilogue (option of the winner) and for the first candidate of a reference tile.
+__device__ __forceinline__ float tri_pair_exact(V3 p, const float4 *rec, float &option)
 {
     const float4 r0 = rec[0], r1 = rec[1], r2 = rec[2];
     const V3 A = xyz(r0), B = xyz(r1), C = xyz(r2);
@@ -101,14 +123,13 @@ __device__ __forceinline__ float tri_pair(V3 p, const float4 *__restrict__ rec, 
         p2 = C;
         option = 3.0f;
     } else if (in_range(uab) && !(dot_s1(xyz(rec[6]), pA) > 0.0f)) {
-        p2 = v3(__fmaf_rn(AB.x, uab, A.x), __fmaf_rn(AB.y, uab, A.y), __fmaf_rn(AB.z, uab, A.z));
+        p2 = fma3(AB, uab, A);
         option = 4.0f;
     } else if (in_range(ubc) && !(dot_s1(xyz(rec[7]), pB) > 0.0f)) {
-        p2 = v3(__fmaf_rn(BC.x, ubc, B.x), __fmaf_rn(BC.y, ubc, B.y), __fmaf_rn(BC.z, ubc, B.z));
+        p2 = fma3(BC, ubc, B);
         option = 5.0f;
     } else if (in_range(uca) && !(dot_s1(xyz(rec[8]), pC) > 0.0f)) {
-        // sic: AB's direction with the CA parameter, tri_distance.cu:180
-        p2 = v3(__fmaf_rn(AB.x, uca, C.x), __fmaf_rn(AB.y, uca, C.y), __fmaf_rn(AB.z, uca, C.z));
+        p2 = fma3(AB, uca, C);  // sic: AB's direction with the CA parameter, tri_distance.cu:180
         option = 6.0f;
     } else {
         const V3 nn = xyz(rec[9]);
@@ -120,94 +141,235 @@ __device__ __forceinline__ float tri_pair(V3 p, const float4 *__restrict__ rec, 
     return dot_s1(df, df);
 }
 
-__global__ void __launch_bounds__(kThreads)
-tri_kernel(int n, const float *__restrict__ xyzp, int m, const float *__restrict__ tri1,
-           const float *__restrict__ tri2, const float *__restrict__ tri3, float *__restrict__ dist,
-           int *__restrict__ point, int *__restrict__ index, int exact)
+// a / b with y = rn(1/b): correctly rounded (== __fdiv_rn) for operands in the safe range.
+__device__ __forceinline__ float div_markstein(float a, float b, float y)
 {
-    __shared__ float4 s_rec[kSubTile * kRecVec];
-    const int bi = blockIdx.y;
-    const float *pp = xyzp + (size_t)bi * n * 3;
-    const size_t tbase = (size_t)bi * m * 3;
+    float q = __fmul_rn(a, y);
+    float r = __fmaf_rn(-b, q, a);
+    q = __fmaf_rn(r, y, q);
+    r = __fmaf_rn(-b, q, a);
+    return __fmaf_rn(r, y, q);
+}
 
-    V3 p[kPR];
-    int row[kPR];
-    float res[kPR], ropt[kPR];
-    int ridx[kPR];
-#pragma unroll
-    for (int r = 0; r < kPR; ++r) {
-        row[r] = (blockIdx.x * kPR + r) * kThreads + threadIdx.x;
-        const int rr = min(row[r], n - 1);
-        p[r] = v3(pp[rr * 3 + 0], pp[rr * 3 + 1], pp[rr * 3 + 2]);
-        res[r] = 0.0f;
-        ropt[r] = 0.0f;
-        ridx[r] = 0;
+struct TriRegs {  // one triangle record in registers (broadcast loads from the warp's slab)
+    V3 A, B, C, AB, BC, CA, xab, xbc, xca, nn;
+    float lab, lbc, lca, rab, rbc, rca;
+    bool safe;
+};
+__device__ __forceinline__ TriRegs load_record(const float4 *rec)
+{
+    TriRegs t;
+    const float4 r0 = rec[0], r1 = rec[1], r2 = rec[2], r3 = rec[3], r4 = rec[4], r5 = rec[5], r6 = rec[6];
+    t.A = xyz(r0), t.B = xyz(r1), t.C = xyz(r2), t.AB = xyz(r3), t.BC = xyz(r4), t.CA = xyz(r5);
+    t.lab = r0.w, t.lbc = r1.w, t.lca = r2.w, t.rab = r3.w, t.rbc = r4.w, t.rca = r5.w;
+    t.xab = xyz(r6), t.xbc = xyz(rec[7]), t.xca = xyz(rec[8]), t.nn = xyz(rec[9]);
+    t.safe = r6.w != 0.0f;
+    return t;
+}
+
+// Branch-free evaluation: the same value tri_pair_exact returns, bit for bit.
+__device__ __forceinline__ float tri_pair_fast(V3 p, const TriRegs &t)
+{
+    const V3 pA = vsub(p, t.A), pB = vsub(p, t.B), pC = vsub(p, t.C);
+    const float nab = dot_s1(pA, t.AB), nbc = dot_s1(pB, t.BC), nca = dot_s1(pC, t.CA);
+    float uab, ubc, uca;
+    const float lo = fminf(fminf(fabsf(nab), fabsf(nbc)), fabsf(nca));
+    const float hi = fmaxf(fmaxf(fabsf(nab), fabsf(nbc)), fabsf(nca));
+    if (t.safe && lo >= kDivLo && hi <= kDivHi) {
+        uab = div_markstein(nab, t.lab, t.rab);
+        ubc = div_markstein(nbc, t.lbc, t.rbc);
+        uca = div_markstein(nca, t.lca, t.rca);
+    } else {  // zero / denormal / huge operands, degenerate triangles: the real thing
+        uab = __fdiv_rn(nab, t.lab);
+        ubc = __fdiv_rn(nbc, t.lbc);
+        uca = __fdiv_rn(nca, t.lca);
     }
+    const bool c1 = (uca > 1.0f) && (uab < 0.0f);
+    const bool c2 = (uab > 1.0f) && (ubc < 0.0f);
+    const bool c3 = (ubc > 1.0f) && (uca < 0.0f);
+    const bool vtx = c1 || c2 || c3;
+    const bool e4 = in_range(uab) && !(dot_s1(t.xab, pA) > 0.0f);
+    const bool e5 = in_range(ubc) && !(dot_s1(t.xbc, pB) > 0.0f);
+    const bool e6 = in_range(uca) && !(dot_s1(t.xca, pC) > 0.0f);
+    // cascade order: vertex A, B, C, edge AB, BC, CA(sic), plane
+    const bool selA = c1 || (!vtx && e4);
+    const bool selB = (!c1 && c2) || (!vtx && !e4 && e5);
+    const bool plane = !vtx && !e4 && !e5 && !e6;
+    // vertex regions are the edge form with parameter 0: S + D*0 == S (D is finite)
+    const float tt = vtx ? 0.0f : (e4 ? uab : (e5 ? ubc : uca));
+    const V3 S = sel3(selA, t.A, sel3(selB, t.B, t.C));
+    const V3 D = sel3(selB, t.BC, t.AB);  // the CA region uses AB's direction (tri_distance.cu:180)
+    const V3 p2e = fma3(D, tt, S);
+    const float dist = dot_s1(pA, t.nn);
+    const V3 p2p = v3(__fmaf_rn(-t.nn.x, dist, p.x), __fmaf_rn(-t.nn.y, dist, p.y), __fmaf_rn(-t.nn.z, dist, p.z));
+    const V3 df = vsub(p, sel3(plane, p2p, p2e));
+    return dot_s1(df, df);
+}
 
-    // exact mode is a flat scan (one "tile" spanning every face): no tail skip, no per-tile restart
-    const int ref_tile = exact ? m : kRefTile;
-    for (int k2 = 0; k2 < m; k2 += ref_tile) {
-        // reference tile bookkeeping, tri_distance.cu:112,127-134
-        const int end_k = min(m, k2 + ref_tile) - k2;
-        const int end_ka = exact ? end_k : end_k - (end_k & 3);
-        float best[kPR], bopt[kPR];
-        int bidx[kPR];
-#pragma unroll
-        for (int r = 0; r < kPR; ++r) {
-            best[r] = 10000.0f;
-            bopt[r] = 0.0f;
-            bidx[r] = 0;
+struct TriArgs {
+    const float *xyz, *t1, *t2, *t3;
+    u64 *keys;              // [b*n]  (distance bits << 32 | face index), 0xff.. = nothing yet
+    unsigned char *poison;  // [b*n]  0xff = clean, 0 = tile 0's first candidate evaluated to NaN
+    unsigned *ticket;       // starts at 0xffffffff
+    int n, m;
+    int ref_tile;           // 512, or m rounded up in exact (flat scan) mode
+    int full_tiles;         // number of complete reference tiles
+    int last_len;           // scanned length of the trailing partial tile (0 = none)
+    int chunk;              // triangles per work unit, a multiple of 32 dividing ref_tile
+    int chunks_per_tile;    // ref_tile / chunk (full tiles)
+    int n_chunks;           // all tiles
+    int n_pblk;             // point blocks per batch item
+    unsigned total_units;
+};
+
+template <int PR>
+__global__ void __launch_bounds__(kThreads, 4) search_kernel(const TriArgs a)
+{
+    __shared__ float4 s_rec[kWarps][32 * kRecVec];
+    const int lane = threadIdx.x & 31;
+    float4 *slab = s_rec[threadIdx.x >> 5];
+
+    for (;;) {
+        unsigned u = 0;
+        if (lane == 0) u = atomicAdd(a.ticket, 1u) + 1u;
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= a.total_units) break;
+        const int ch = (int)(u % (unsigned)a.n_chunks);
+        const unsigned pu = u / (unsigned)a.n_chunks;
+        const int bi = (int)(pu / (unsigned)a.n_pblk);
+        const int pbase = (int)(pu % (unsigned)a.n_pblk) * (32 * PR);
+        // chunk -> (reference tile start k2, offset inside the tile, length)
+        int k2, off, len;
+        if (ch < a.full_tiles * a.chunks_per_tile) {
+            k2 = (ch / a.chunks_per_tile) * a.ref_tile;
+            off = (ch % a.chunks_per_tile) * a.chunk;
+            len = a.chunk;
+        } else {
+            k2 = a.full_tiles * a.ref_tile;
+            off = (ch - a.full_tiles * a.chunks_per_tile) * a.chunk;
+            len = min(a.chunk, a.last_len - off);
         }
-        for (int s0 = 0; s0 < end_ka; s0 += kSubTile) {
-            const int ts = min(kSubTile, end_ka - s0);
-            __syncthreads();
-            for (int t = threadIdx.x; t < ts; t += kThreads) {
-                const size_t g = tbase + (size_t)(k2 + s0 + t) * 3;
-                build_record(&s_rec[t * kRecVec], v3(tri1[g], tri1[g + 1], tri1[g + 2]),
-                             v3(tri2[g], tri2[g + 1], tri2[g + 2]), v3(tri3[g], tri3[g + 1], tri3[g + 2]));
-            }
-            __syncthreads();
-            for (int k = 0; k < ts; ++k) {
-                const float4 *rec = &s_rec[k * kRecVec];
-                const bool first = (s0 + k) == 0;
+        const size_t tbase = (size_t)bi * a.m * 3;
+        const float *pp = a.xyz + (size_t)bi * a.n * 3;
+
+        V3 p[PR];
+        float best[PR];
+        int bidx[PR];
+        bool live[PR];  // false: this tile's first candidate is NaN for the point -> the tile is void
 #pragma unroll
-                for (int r = 0; r < kPR; ++r) {
-                    float opt;
-                    const float d = tri_pair(p[r], rec, opt);
-                    if (first || d < best[r]) {  // tri_distance.cu:194
+        for (int r = 0; r < PR; ++r) {
+            const int row = min(pbase + r * 32 + lane, a.n - 1);
+            p[r] = v3(pp[row * 3 + 0], pp[row * 3 + 1], pp[row * 3 + 2]);
+        }
+        // The reference takes the first candidate of every 512-tile unconditionally
+        // (tri_distance.cu:194, k == 0): if it evaluates to NaN nothing in that tile can replace it.
+        {
+            const size_t g = tbase + (size_t)k2 * 3;
+            if (lane == 0)
+                build_record(slab, v3(a.t1[g], a.t1[g + 1], a.t1[g + 2]), v3(a.t2[g], a.t2[g + 1], a.t2[g + 2]),
+                             v3(a.t3[g], a.t3[g + 1], a.t3[g + 2]));
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < PR; ++r) {
+                float opt;
+                const float d0 = tri_pair_exact(p[r], slab, opt);
+                live[r] = !(d0 != d0);
+                best[r] = (off == 0) ? d0 : __int_as_float(0x7f800000);  // candidate k2 belongs to chunk 0
+                bidx[r] = k2;
+            }
+            __syncwarp();
+        }
+
+        for (int s0 = 0; s0 < len; s0 += 32) {
+            const int cnt = min(32, len - s0);
+            if (lane < cnt) {
+                const size_t g = tbase + (size_t)(k2 + off + s0 + lane) * 3;
+                build_record(slab + lane * kRecVec, v3(a.t1[g], a.t1[g + 1], a.t1[g + 2]),
+                             v3(a.t2[g], a.t2[g + 1], a.t2[g + 2]), v3(a.t3[g], a.t3[g + 1], a.t3[g + 2]));
+            }
+            __syncwarp();
+#pragma unroll 1
+            for (int j = 0; j < cnt; ++j) {
+                const TriRegs t = load_record(slab + j * kRecVec);
+                const int fi = k2 + off + s0 + j;
+#pragma unroll
+                for (int r = 0; r < PR; ++r) {
+                    const float d = tri_pair_fast(p[r], t);
+                    if (d < best[r]) {  // NaN never wins; ascending scan + strict '<' = lowest index on ties
                         best[r] = d;
-                        bopt[r] = opt;
-                        bidx[r] = k2 + s0 + k;
+                        bidx[r] = fi;
                     }
                 }
             }
+            __syncwarp();
         }
+
 #pragma unroll
-        for (int r = 0; r < kPR; ++r) {
-            if (k2 == 0 || res[r] > best[r]) {  // tri_distance.cu:202
-                res[r] = best[r];
-                ropt[r] = bopt[r];
-                ridx[r] = bidx[r];
+        for (int r = 0; r < PR; ++r) {
+            const int row = pbase + r * 32 + lane;
+            if (row >= a.n) continue;
+            const size_t o = (size_t)bi * a.n + row;
+            if (live[r]) {
+                if (best[r] < __int_as_float(0x7f800000) || off == 0)
+                    key_min(&a.keys[o], make_key(best[r], (unsigned)bidx[r]));
+            } else if (k2 == 0 && off == 0) {
+                a.poison[o] = 0;
             }
         }
     }
-#pragma unroll
-    for (int r = 0; r < kPR; ++r) {
-        if (row[r] < n) {
-            const size_t o = (size_t)bi * n + row[r];
-            if (dist) dist[o] = res[r];
-            point[o] = (int)ropt[r];
-            index[o] = ridx[r];
+}
+
+struct FinishArgs {
+    const float *xyz, *t1, *t2, *t3;
+    const u64 *keys;
+    const unsigned char *poison;
+    float *dist;
+    int *point, *index;
+    int b, n, m;
+    int empty_tail;  // the trailing reference tile holds 1-3 triangles: its (10000, 0, 0) wins over d > 10000
+};
+
+// Decode the winner per point and recompute its region option with the exact cascade.
+__global__ void __launch_bounds__(256) finish_kernel(const FinishArgs a)
+{
+    const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (t >= (long long)a.b * a.n) return;
+    const int bi = (int)(t / a.n);
+    const u64 key = a.keys[t];
+    float d = 10000.0f, opt = 0.0f;  // tri_distance.cu:127-128 with nothing scanned
+    int idx = 0;
+    const bool poisoned = a.poison[t] == 0;
+    if (poisoned || key != ~0ull) {
+        idx = poisoned ? 0 : (int)(unsigned)key;
+        const size_t g = ((size_t)bi * a.m + idx) * 3;
+        float4 rec[kRecVec];
+        build_record(rec, v3(a.t1[g], a.t1[g + 1], a.t1[g + 2]), v3(a.t2[g], a.t2[g + 1], a.t2[g + 2]),
+                     v3(a.t3[g], a.t3[g + 1], a.t3[g + 2]));
+        d = tri_pair_exact(v3(a.xyz[t * 3], a.xyz[t * 3 + 1], a.xyz[t * 3 + 2]), rec, opt);
+        if (a.empty_tail && d > 10000.0f) {  // merge rule `dist > best` against the empty tile, :202
+            d = 10000.0f;
+            opt = 0.0f;
+            idx = 0;
         }
     }
+    if (a.dist) a.dist[t] = d;
+    a.point[t] = (int)opt;
+    a.index[t] = idx;
 }
 
 }  // namespace tri
 }  // namespace geom
 
-extern "C" int geom_tri_fwd(int b, int n, const float *xyz, int m, const float *tri1,
-                            const float *tri2, const float *tri3, float *dist, int *point,
-                            int *index, unsigned flags, geom_stream_t stream)
+extern "C" size_t geom_tri_workspace_bytes(int b, int n)
+{
+    if (b < 0 || n < 0) return 0;
+    const size_t pts = (size_t)b * n;
+    return sizeof(geom::u64) * pts + ((pts + 15) & ~(size_t)15) + 16;  // keys + poison bytes + ticket
+}
+
+extern "C" int geom_tri_fwd(int b, int n, const float *xyz, int m, const float *tri1, const float *tri2,
+                            const float *tri3, float *dist, int *point, int *index, void *workspace,
+                            size_t workspace_bytes, unsigned flags, geom_stream_t stream)
 {
     using namespace geom;
     using namespace geom::tri;
@@ -216,22 +378,101 @@ extern "C" int geom_tri_fwd(int b, int n, const float *xyz, int m, const float *
     if (b == 0 || n == 0) return GEOM_OK;
     if (!xyz || !point || !index) return GEOM_ERR_INVALID_ARG;
     if (m > 0 && (!tri1 || !tri2 || !tri3)) return GEOM_ERR_INVALID_ARG;
-    if (b > 65535) return GEOM_ERR_INVALID_ARG;
     cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaSuccess;
     if (m == 0) {
         // the reference kernel's tile loop never runs: outputs keep the caller's zeros
-        cudaError_t e = cudaSuccess;
         if (dist) e = cudaMemsetAsync(dist, 0, sizeof(float) * (size_t)b * n, st);
         if (e == cudaSuccess) e = cudaMemsetAsync(point, 0, sizeof(int) * (size_t)b * n, st);
         if (e == cudaSuccess) e = cudaMemsetAsync(index, 0, sizeof(int) * (size_t)b * n, st);
         return status_from_cuda(e);
     }
-    const int per_cta = kThreads * kPR;
-    dim3 grid((n + per_cta - 1) / per_cta, b);
-    {
+    const size_t need = geom_tri_workspace_bytes(b, n);
+    if (!workspace || workspace_bytes < need || ((uintptr_t)workspace & 7u)) return GEOM_ERR_WORKSPACE;
+    const bool exact = (flags & GEOM_FLAG_EXACT_TAIL) != 0;
+    const size_t pts = (size_t)b * n;
+
+    TriArgs a;
+    a.xyz = xyz;
+    a.t1 = tri1;
+    a.t2 = tri2;
+    a.t3 = tri3;
+    a.keys = (u64 *)workspace;
+    a.poison = (unsigned char *)(a.keys + pts);
+    a.ticket = (unsigned *)(a.poison + ((pts + 15) & ~(size_t)15));
+    a.n = n;
+    a.m = m;
+    // exact mode is a flat scan: one "tile" spanning every face, no tail skip, no per-tile restart
+    a.ref_tile = exact ? ((m + 511) / 512) * 512 : kRefTile;
+    a.full_tiles = exact ? 0 : m / kRefTile;
+    const int rem = m - a.full_tiles * a.ref_tile;
+    a.last_len = exact ? m : rem - (rem & 3);  // tri_distance.cu:129
+    const int empty_tail = (!exact && a.full_tiles > 0 && rem > 0 && a.last_len == 0) ? 1 : 0;
+
+    int dev = 0, sms = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return status_from_cuda(e);
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return status_from_cuda(e);
+    const long long slots = (long long)sms * 4 * kWarps;
+    // Largest points-per-lane / chunk that still gives every warp ~3 units to pull.
+    int pr = 4, chunk = 512;
+    auto units_for = [&](int pr_, int chunk_) {
+        const long long nch = (long long)a.full_tiles * (a.ref_tile / chunk_) + (a.last_len + chunk_ - 1) / chunk_;
+        return (long long)b * ((n + 32 * pr_ - 1) / (32 * pr_)) * nch;
+    };
+    while (units_for(pr, chunk) < 3 * slots) {
+        if (pr > 1)
+            pr >>= 1;
+        else if (chunk > 64)
+            chunk >>= 1;
+        else
+            break;
+    }
+    if (const char *env = getenv("GEOM_TRI_TUNE")) {  // "pr,chunk": force a variant (tests / tuning)
+        int epr = 0, ech = 0;
+        if (sscanf(env, "%d,%d", &epr, &ech) == 2 && (epr == 1 || epr == 2 || epr == 4) &&
+            (ech == 64 || ech == 128 || ech == 256 || ech == 512)) {
+            pr = epr;
+            chunk = ech;
+        }
+    }
+    a.chunk = chunk;
+    a.chunks_per_tile = a.ref_tile / chunk;
+    a.n_chunks = a.full_tiles * a.chunks_per_tile + (a.last_len + chunk - 1) / chunk;
+    a.n_pblk = (n + 32 * pr - 1) / (32 * pr);
+    const long long units = units_for(pr, chunk);
+    if (units > 0x7fffffffLL) return GEOM_ERR_INVALID_ARG;
+    a.total_units = (unsigned)units;
+
+    if ((e = cudaMemsetAsync(workspace, 0xff, need, st)) != cudaSuccess) return status_from_cuda(e);
+    if (units > 0) {
+        const int ctas = (int)(((units < slots ? units : slots) + kWarps - 1) / kWarps);
         prof::Scope ps(st, prof::kTri);
-        tri_kernel<<<grid, kThreads, 0, st>>>(n, xyz, m, tri1, tri2, tri3, dist, point, index,
-                                              (flags & GEOM_FLAG_EXACT_TAIL) ? 1 : 0);
+        if (pr == 4)
+            search_kernel<4><<<ctas, kThreads, 0, st>>>(a);
+        else if (pr == 2)
+            search_kernel<2><<<ctas, kThreads, 0, st>>>(a);
+        else
+            search_kernel<1><<<ctas, kThreads, 0, st>>>(a);
+    }
+    if ((e = cudaGetLastError()) != cudaSuccess) return status_from_cuda(e);
+
+    FinishArgs f;
+    f.xyz = xyz;
+    f.t1 = tri1;
+    f.t2 = tri2;
+    f.t3 = tri3;
+    f.keys = a.keys;
+    f.poison = a.poison;
+    f.dist = dist;
+    f.point = point;
+    f.index = index;
+    f.b = b;
+    f.n = n;
+    f.m = m;
+    f.empty_tail = empty_tail;
+    {
+        prof::Scope ps(st, prof::kMisc);
+        finish_kernel<<<(unsigned)((pts + 255) / 256), 256, 0, st>>>(f);
     }
     return status_from_cuda(cudaGetLastError());
 }

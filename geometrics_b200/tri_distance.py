@@ -12,7 +12,7 @@ import torch
 from . import _lib
 
 
-def tri_forward(xyz1, tri1, tri2, tri3, *, exact_tail: bool = False):
+def tri_forward(xyz1, tri1, tri2, tri3, *, exact_tail: bool = False, want_dist: bool = True):
     _lib.require_cuda_f32("xyz1", xyz1, 3)
     for name, t in (("tri1", tri1), ("tri2", tri2), ("tri3", tri3)):
         _lib.require_cuda_f32(name, t, 3)
@@ -28,11 +28,14 @@ def tri_forward(xyz1, tri1, tri2, tri3, *, exact_tail: bool = False):
     m = tri1.shape[1]
     dev = xyz1.device
     with torch.cuda.device(dev):
-        dist = torch.empty((b, n), dtype=torch.float32, device=dev)
+        dist = torch.empty((b, n), dtype=torch.float32, device=dev) if want_dist else None
         point = torch.empty((b, n), dtype=torch.int32, device=dev)
         index = torch.empty((b, n), dtype=torch.int32, device=dev)
+        ws_bytes = L.geom_tri_workspace_bytes(b, n)
+        ws = torch.empty(ws_bytes // 8 + 1, dtype=torch.int64, device=dev)
         st = L.geom_tri_fwd(b, n, xyz1.data_ptr(), m, tri1.data_ptr(), tri2.data_ptr(), tri3.data_ptr(),
-                            dist.data_ptr(), point.data_ptr(), index.data_ptr(),
+                            dist.data_ptr() if want_dist else None, point.data_ptr(), index.data_ptr(),
+                            ws.data_ptr(), ws.numel() * 8,
                             _lib.GEOM_FLAG_EXACT_TAIL if exact_tail else 0, _lib.current_stream_ptr(dev))
         _lib.check(st, "geom_tri_fwd")
     return dist, point, index

@@ -115,11 +115,12 @@ GEOM_API int geom_chamfer_loss_bwd(int b, int n, const float *xyz1, int m, const
  * them, point = region code 0..6 (0 interior, 1/2/3 vertex A/B/C, 4/5/6 edge AB/BC/CA),
  * index = face index.  Arithmetic and quirks (option-6 direction vector, NaN tile poisoning,
  * best=10000 initialisation) follow tri_distance.cu:124-206 as compiled; see DESIGN.md.
- * No workspace.
+ * dist may be NULL.  workspace >= geom_tri_workspace_bytes(b, n), 8-byte aligned.
  * ------------------------------------------------------------------------------------------- */
+GEOM_API size_t geom_tri_workspace_bytes(int b, int n);
 GEOM_API int geom_tri_fwd(int b, int n, const float *xyz, int m, const float *tri1, const float *tri2,
                  const float *tri3, float *dist, int *point, int *index,
-                 unsigned flags, geom_stream_t stream);
+                 void *workspace, size_t workspace_bytes, unsigned flags, geom_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Point-to-surface loss on the search result (forward sum, backward scatter to the vertices).

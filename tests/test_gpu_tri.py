@@ -52,6 +52,22 @@ def test_oracle_matches_reference_cuda(oracle, ref_cuda, cuda):
         _cmp(got, tuple(t.cpu().numpy() for t in want), f"oracle {case}")
 
 
+@pytest.mark.parametrize("tune", ["1,64", "1,512", "2,128", "2,512", "4,256", "4,512"])
+def test_every_kernel_variant(oracle, cuda, tune, monkeypatch):
+    """Points-per-lane and chunk-size variants (normally picked from the problem size) all give the
+    reference's answer, on cases that exercise tile poisoning, the tail skip and multi-tile merges."""
+    import geometrics_b200 as g
+
+    monkeypatch.setenv("GEOM_TRI_TUNE", tune)
+    for case in [("degenerate0", 1, 200, 1100, 28), ("big", 1, 257, 2466, 30), ("onmesh", 2, 600, 960, 29),
+                 ("random", 2, 513, 1030, 23), ("random", 1, 300, 515, 24)]:
+        pts, t1, t2, t3 = tri_inputs(*case)
+        for exact in (False, True):
+            got = g.tri_forward(*(t.to(cuda) for t in (pts, t1, t2, t3)), exact_tail=exact)
+            want = oracle.tri_fwd(pts.numpy(), t1.numpy(), t2.numpy(), t3.numpy(), exact=exact)
+            _cmp(tuple(t.cpu().numpy() for t in got), want, f"{tune} {case} exact={exact}")
+
+
 def test_module_surface(cuda):
     """TriDistance()(xyz1, tri1, tri2, tri3) -> (dist f32, point i32, index i32), all (B,n); the
     caller's gathers (utils.py:467-469) produce tensors with requires_grad."""
@@ -81,7 +97,10 @@ def test_argument_errors(cuda):
     with pytest.raises(TypeError):
         g.tri_forward(p.half(), t, t, t)
     assert g.lib().geom_tri_fwd(2, 8, p.data_ptr(), 4, t.data_ptr(), t.data_ptr(), t.data_ptr(),
-                                None, None, None, 0, None) == -1
+                                None, None, None, None, 0, 0, None) == -1
+    i = torch.zeros(2, 8, dtype=torch.int32, device=cuda)
+    assert g.lib().geom_tri_fwd(2, 8, p.data_ptr(), 4, t.data_ptr(), t.data_ptr(), t.data_ptr(),
+                                None, i.data_ptr(), i.data_ptr(), None, 0, 0, None) == -2  # workspace missing
     # no faces: outputs are the zeros the reference's caller pre-allocates (tri_distance.py:22-30)
     d, pt, ix = g.tri_forward(p, *(torch.zeros(2, 0, 3, device=cuda),) * 3)
     assert (d == 0).all() and (pt == 0).all() and (ix == 0).all()
