@@ -318,7 +318,7 @@ def run_product(args):
             "clocks": clocks,
             "e2e": {"value": pairs_step / e2e_s, "unit": UNIT, "h2d_bytes_per_step": hx1.numel() * 4 + hx2.numel() * 4,
                     "d2h_bytes_per_step": hi1.numel() * 4 + hi2.numel() * 4, "ms_per_step": e2e_s * 1e3,
-                    "api": "geometrics_b200.chamfer_forward_host (pinned host in/out)", "steps": e2e_steps},
+                    "api": "geom_chamfer_fwd_host via geometrics_b200.chamfer_forward_host (pinned host in/out, 4 batch chunks pipelined)", "steps": e2e_steps},
             "gpu_launches": launches,
             "kernels": {k_: {"ms_per_launch": v[0] / v[1], "launches": v[1], "share_of_step": v[0] / args.steps / ms_step}
                         for k_, v in kern.items()},

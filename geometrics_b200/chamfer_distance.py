@@ -66,80 +66,62 @@ class ChamferDistance(torch.nn.Module):
 
 
 # ------------------------------------------------------------------------------------------------
-# Host-buffer entry: pinned host point sets in, indices out.
+# Host-buffer entry: pinned host point sets in, indices out (geom_chamfer_fwd_host).
 # ------------------------------------------------------------------------------------------------
-_host_state = {}
+_host_ctx = {}
 
 
-def _host_pipe(dev, b, n, m, chunks):
-    key = (dev.index, b, n, m, chunks)
-    st = _host_state.get(key)
-    if st is None:
-        L = _lib.lib()
-        per = (b + chunks - 1) // chunks
-        st = dict(
-            per=per,
-            h2d=torch.cuda.Stream(dev), comp=torch.cuda.Stream(dev), d2h=torch.cuda.Stream(dev),
-            x1=torch.empty((b, n, 3), dtype=torch.float32, device=dev),
-            x2=torch.empty((b, m, 3), dtype=torch.float32, device=dev),
-            i1=torch.empty((b, n), dtype=torch.int32, device=dev),
-            i2=torch.empty((b, m), dtype=torch.int32, device=dev),
-            ws_bytes=L.geom_chamfer_workspace_bytes(per, n, m),
-            ev_in=[torch.cuda.Event() for _ in range(chunks)],
-            ev_out=[torch.cuda.Event() for _ in range(chunks)],
-        )
-        st["ws"] = [torch.empty(max(st["ws_bytes"] // 8, 1), dtype=torch.int64, device=dev) for _ in range(chunks)]
-        _host_state.clear()  # keep one shape resident
-        _host_state[key] = st
-    return st
+def _ctx_for(dev: torch.device):
+    """One geom_host_ctx (streams + reusable device arena) per (device, thread)."""
+    import ctypes
+    import threading
+
+    key = (dev.index, threading.get_ident())
+    ctx = _host_ctx.get(key)
+    if ctx is None:
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().geom_host_ctx_create(ctypes.byref(handle)), "geom_host_ctx_create")
+        ctx = _host_ctx[key] = handle
+    return ctx
 
 
 def chamfer_forward_host(xyz1: torch.Tensor, xyz2: torch.Tensor, idx1_out: torch.Tensor, idx2_out: torch.Tensor,
-                         device=None, chunks: int = 4, exact_tail: bool = False):
+                         device=None, chunks: int = 4, exact_tail: bool = False, dist1_out=None, dist2_out=None):
     """ChamferDistance on HOST tensors: ``xyz1`` (B,n,3) / ``xyz2`` (B,m,3) fp32 CPU tensors (pinned
-    memory for full copy/compute overlap) -> ``idx1_out`` (B,n) / ``idx2_out`` (B,m) int32 CPU tensors.
+    memory for full copy/compute overlap) -> ``idx1_out`` (B,n) / ``idx2_out`` (B,m) int32 CPU tensors
+    (and optionally the squared distances).
 
-    The batch is cut into ``chunks`` slices; slice c+1 is copied to the device while slice c is
-    searched and slice c-1's indices are copied back (three streams).  Returns when every index is in
-    host memory.  This is the end-to-end path bench.py times (``e2e``)."""
-    if xyz1.is_cuda or xyz2.is_cuda or idx1_out.is_cuda or idx2_out.is_cuda:
-        raise RuntimeError("chamfer_forward_host takes CPU tensors; use chamfer_forward for device tensors")
+    One call into the C ABI (``geom_chamfer_fwd_host``): the batch is cut into ``chunks`` slices; slice
+    c+1 is copied to the device while slice c is searched and slice c-1's indices are copied back
+    (three streams owned by the library).  Returns when every result is in host memory.  This is the
+    end-to-end path bench.py times (``e2e``)."""
+    tensors = [("xyz1", xyz1), ("xyz2", xyz2), ("idx1_out", idx1_out), ("idx2_out", idx2_out)]
+    tensors += [(nm, t) for nm, t in (("dist1_out", dist1_out), ("dist2_out", dist2_out)) if t is not None]
+    for name, t in tensors:
+        if t.is_cuda:
+            raise RuntimeError(f"{name}: chamfer_forward_host takes CPU tensors; use chamfer_forward for device tensors")
+        if not t.is_contiguous():
+            raise ValueError(f"{name} must be contiguous")
     for name, t in (("xyz1", xyz1), ("xyz2", xyz2)):
-        if t.dtype != torch.float32 or t.dim() != 3 or t.shape[-1] != 3 or not t.is_contiguous():
-            raise ValueError(f"{name} must be a contiguous float32 (B,N,3) tensor")
+        if t.dtype != torch.float32 or t.dim() != 3 or t.shape[-1] != 3:
+            raise ValueError(f"{name} must be a float32 (B,N,3) tensor")
     b, n, _ = xyz1.shape
     m = xyz2.shape[1]
     if xyz2.shape[0] != b:
         raise ValueError("batch mismatch")
-    for name, t, cnt in (("idx1_out", idx1_out, n), ("idx2_out", idx2_out, m)):
-        if t.dtype != torch.int32 or tuple(t.shape) != (b, cnt) or not t.is_contiguous():
-            raise ValueError(f"{name} must be a contiguous int32 ({b},{cnt}) tensor")
+    for name, t, cnt, dt in (("idx1_out", idx1_out, n, torch.int32), ("idx2_out", idx2_out, m, torch.int32),
+                             ("dist1_out", dist1_out, n, torch.float32), ("dist2_out", dist2_out, m, torch.float32)):
+        if t is not None and (t.dtype != dt or tuple(t.shape) != (b, cnt)):
+            raise ValueError(f"{name} must be a {dt} ({b},{cnt}) tensor")
+    if not torch.cuda.is_available():
+        raise RuntimeError("no CUDA device (geometrics_b200 has no CPU path)")
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-    if b == 0:
-        return idx1_out, idx2_out
     L = _lib.lib()
-    chunks = max(1, min(chunks, b))
-    st = _host_pipe(dev, b, n, m, chunks)
-    per = st["per"]
-    flags = _lib.GEOM_FLAG_EXACT_TAIL if exact_tail else 0
     with torch.cuda.device(dev):
-        for c in range(chunks):
-            lo, hi = c * per, min(b, (c + 1) * per)
-            if lo >= hi:
-                break
-            with torch.cuda.stream(st["h2d"]):
-                st["x1"][lo:hi].copy_(xyz1[lo:hi], non_blocking=True)
-                st["x2"][lo:hi].copy_(xyz2[lo:hi], non_blocking=True)
-                st["ev_in"][c].record(st["h2d"])
-            st["comp"].wait_event(st["ev_in"][c])
-            rc = L.geom_chamfer_fwd(hi - lo, n, st["x1"][lo:hi].data_ptr(), m, st["x2"][lo:hi].data_ptr(),
-                                    None, st["i1"][lo:hi].data_ptr(), None, st["i2"][lo:hi].data_ptr(),
-                                    st["ws"][c].data_ptr(), st["ws_bytes"], flags, st["comp"].cuda_stream)
-            _lib.check(rc, "geom_chamfer_fwd")
-            st["ev_out"][c].record(st["comp"])
-            st["d2h"].wait_event(st["ev_out"][c])
-            with torch.cuda.stream(st["d2h"]):
-                idx1_out[lo:hi].copy_(st["i1"][lo:hi], non_blocking=True)
-                idx2_out[lo:hi].copy_(st["i2"][lo:hi], non_blocking=True)
-        st["d2h"].synchronize()
+        rc = L.geom_chamfer_fwd_host(_ctx_for(dev), b, n, xyz1.data_ptr(), m, xyz2.data_ptr(),
+                                     dist1_out.data_ptr() if dist1_out is not None else None, idx1_out.data_ptr(),
+                                     dist2_out.data_ptr() if dist2_out is not None else None, idx2_out.data_ptr(),
+                                     int(chunks), _lib.GEOM_FLAG_EXACT_TAIL if exact_tail else 0)
+    _lib.check(rc, "geom_chamfer_fwd_host")
     return idx1_out, idx2_out

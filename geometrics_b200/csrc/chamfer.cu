@@ -52,35 +52,63 @@ struct TwoWayArgs {
 // One warp = one worker.  Work units (row block of 32*R xyz1 rows) x (strip of column tiles) are
 // handed out by a global ticket counter, so every warp stays busy until the whole search is done
 // (a static split leaves the SM sub-partitions' lower-priority warps running alone at the end).
-template <int R, int MINB, int TILE>
+// The next column tile (of this unit, or the first tile of the next unit, whose ticket is drawn
+// early) is prefetched with LDGSTS into a raw per-warp buffer while the current tile is evaluated.
+//   ORD = 0: the compiler schedules the packed-FP32 stream; ORD = 1: phased `asm volatile` order
+//   (8 independent chains per phase, dependent operations 8 issues apart).
+template <int R, int MINB, int TILE, int ORD>
 __global__ void __launch_bounds__(kThreads, MINB) twoway_kernel(const TwoWayArgs a)
 {
     constexpr int kRowsPerWarp = 32 * R;
     // Per-warp private staging: candidate tile as duplicated SoA pairs {v,v} so one 64-bit register
-    // pair feeds a packed op against two different rows; and the tile's column minima.
+    // pair feeds a packed op against two different rows; the tile's column minima; the raw prefetch.
     __shared__ __align__(16) float2 s_q[kWarps][3][TILE];
     __shared__ __align__(16) unsigned s_col[kWarps][TILE];
+    __shared__ __align__(16) float s_raw[kWarps][3 * TILE];
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     float2(*sq)[TILE] = s_q[warp];
     unsigned *scol = s_col[warp];
+    float *raw = s_raw[warp];
 
     u64 nx[R / 2], ny[R / 2], nz[R / 2];  // negated row coordinates, rows (2i, 2i+1) packed
     float best[R];
     unsigned grp[R];
 
-    for (;;) {
-        unsigned u = 0;
-        if (lane == 0) u = atomicAdd(a.ticket, 1u) + 1u;
-        u = __shfl_sync(0xffffffffu, u, 0);
-        if (u >= a.total_units) break;
+    auto fetch = [&]() {
+        unsigned t = 0;
+        if (lane == 0) t = atomicAdd(a.ticket, 1u) + 1u;
+        return __shfl_sync(0xffffffffu, t, 0);
+    };
+    // asynchronous copy of column tile `ct` of batch item `bi_` into the raw buffer (AoS, tc*3 floats)
+    auto prefetch = [&](int bi_, int ct) {
+        const int c0 = ct * a.tile_cols;
+        const int tc = min(a.tile_cols, a.m - c0);
+        const float *p2 = a.xyz2 + ((size_t)bi_ * a.m_full + c0) * 3;
+        for (int e = lane; e < tc * 3; e += 32) cp_async4(&raw[e], &p2[e]);
+        cp_async_commit();
+    };
+    auto first_tile = [&](unsigned u_, int &bi_, int &ct_) {
+        const unsigned rid = u_ / (unsigned)a.strips_per_row;
+        bi_ = (int)(rid / (unsigned)a.n_rblk);
+        ct_ = (int)(u_ % (unsigned)a.strips_per_row) * a.strip;
+    };
+
+    unsigned u = fetch();
+    if (u < a.total_units) {
+        int b0, c0;
+        first_tile(u, b0, c0);
+        prefetch(b0, c0);
+    }
+    while (u < a.total_units) {
         const unsigned rid = u / (unsigned)a.strips_per_row;
         const int ct0 = (int)(u % (unsigned)a.strips_per_row) * a.strip;
         const int ct1 = min(ct0 + a.strip, a.n_ctile);
         const int bi = (int)(rid / (unsigned)a.n_rblk);
         const int rb = (int)(rid % (unsigned)a.n_rblk);
         const int rbase = rb * kRowsPerWarp;
+        unsigned u_next = a.total_units;
         {
             const float *p1 = a.xyz1 + (size_t)bi * a.n_full * 3;
 #pragma unroll
@@ -100,21 +128,33 @@ __global__ void __launch_bounds__(kThreads, MINB) twoway_kernel(const TwoWayArgs
         }
 
         for (int ct = ct0; ct < ct1; ++ct) {
-            // ---- stage the candidate tile ----
+            // ---- raw tile (prefetched) -> duplicated SoA pairs ----
             const int c0 = ct * a.tile_cols;
             const int tc = min(a.tile_cols, a.m - c0);
             const int ngroups = (tc + kGroupCols - 1) / kGroupCols;
+            cp_async_wait_all();
+            __syncwarp();
             {
-                const float *p2 = a.xyz2 + ((size_t)bi * a.m_full + c0) * 3;
                 const int nel = ngroups * kGroupCols * 3;
                 for (int e = lane; e < nel; e += 32) {
                     const int pt = e / 3;
                     const int c = e - pt * 3;
-                    const float v = p2[min(pt, tc - 1) * 3 + c];  // padding = duplicate of the last column
+                    const float v = raw[min(pt, tc - 1) * 3 + c];  // padding = duplicate of the last column
                     sq[c][pt] = make_float2(v, v);
                 }
             }
             __syncwarp();
+            // ---- prefetch what this warp evaluates next ----
+            if (ct + 1 < ct1) {
+                prefetch(bi, ct + 1);
+            } else {
+                u_next = fetch();
+                if (u_next < a.total_units) {
+                    int bn, cn;
+                    first_tile(u_next, bn, cn);
+                    prefetch(bn, cn);
+                }
+            }
 
             // ---- all pairs of (32*R rows) x (tile columns) ----
             const unsigned gid0 = (unsigned)(c0 / kGroupCols);
@@ -136,15 +176,50 @@ __global__ void __launch_bounds__(kThreads, MINB) twoway_kernel(const TwoWayArgs
                     const u64 qy[4] = {ya.x, ya.y, yb.x, yb.y};
                     const u64 qz[4] = {za.x, za.y, zb.x, zb.y};
                     float d[4][R];  // [column][row]
+                    if (ORD == 0) {
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
+                        for (int c = 0; c < 4; ++c) {
 #pragma unroll
-                        for (int i = 0; i < R / 2; ++i) {
-                            const u64 dx = add2(qx[c], nx[i]);
-                            const u64 dy = add2(qy[c], ny[i]);
-                            const u64 dz = add2(qz[c], nz[i]);
-                            const u64 dd = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
-                            unpack2(dd, d[c][2 * i], d[c][2 * i + 1]);
+                            for (int i = 0; i < R / 2; ++i) {
+                                const u64 dx = add2(qx[c], nx[i]);
+                                const u64 dy = add2(qy[c], ny[i]);
+                                const u64 dz = add2(qz[c], nz[i]);
+                                const u64 dd = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
+                                unpack2(dd, d[c][2 * i], d[c][2 * i + 1]);
+                            }
+                        }
+                    } else {
+                        // two columns at a time: R independent chains, each phase R issues long
+#pragma unroll
+                        for (int ch = 0; ch < 2; ++ch) {
+                            u64 t[2][R / 2], w[2][R / 2];
+#pragma unroll
+                            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                                for (int i = 0; i < R / 2; ++i) w[c][i] = add2v(qy[ch * 2 + c], ny[i]);
+#pragma unroll
+                            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                                for (int i = 0; i < R / 2; ++i) t[c][i] = add2v(qx[ch * 2 + c], nx[i]);
+#pragma unroll
+                            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                                for (int i = 0; i < R / 2; ++i) w[c][i] = mul2v(w[c][i], w[c][i]);
+#pragma unroll
+                            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                                for (int i = 0; i < R / 2; ++i) w[c][i] = fma2v(t[c][i], t[c][i], w[c][i]);
+#pragma unroll
+                            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                                for (int i = 0; i < R / 2; ++i) t[c][i] = add2v(qz[ch * 2 + c], nz[i]);
+#pragma unroll
+                            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                                for (int i = 0; i < R / 2; ++i) {
+                                    w[c][i] = fma2v(t[c][i], t[c][i], w[c][i]);
+                                    unpack2(w[c][i], d[ch * 2 + c][2 * i], d[ch * 2 + c][2 * i + 1]);
+                                }
                         }
                     }
 #pragma unroll
@@ -191,6 +266,7 @@ __global__ void __launch_bounds__(kThreads, MINB) twoway_kernel(const TwoWayArgs
             const int row = rbase + r * 32 + lane;
             if (row < a.n) key_min(&rk[row], make_key(best[r], grp[r]));
         }
+        u = u_next;
     }
 }
 
@@ -369,7 +445,7 @@ struct Tune {
 };
 static Tune read_tune()
 {
-    Tune t = {0, 2, 0};
+    Tune t = {1, 2, 0};  // phased FP2 order, 256-column tiles, strips of 2 (profiles/r01_chamfer_tune_v2.jsonl)
     if (const char *e = getenv("GEOM_CHAMFER_TUNE")) {
         int v = 0, s = 0, tc = 0;
         const int got = sscanf(e, "%d,%d,%d", &v, &s, &tc);
@@ -429,11 +505,11 @@ extern "C" int geom_chamfer_fwd(int b, int n, const float *xyz1, int m, const fl
             void (*kernel)(const TwoWayArgs);
         };
         static const Variant kVariants[] = {
-            {8, 4, 256, twoway_kernel<8, 4, 256>},
-            {4, 8, 128, twoway_kernel<4, 8, 128>},
-            {4, 6, 256, twoway_kernel<4, 6, 256>},
-            {8, 3, 256, twoway_kernel<8, 3, 256>},
-            {6, 5, 256, twoway_kernel<6, 5, 256>},
+            {8, 4, 256, twoway_kernel<8, 4, 256, 0>},
+            {8, 4, 256, twoway_kernel<8, 4, 256, 1>},
+            {8, 4, 128, twoway_kernel<8, 4, 128, 0>},
+            {8, 4, 128, twoway_kernel<8, 4, 128, 1>},
+            {8, 3, 256, twoway_kernel<8, 3, 256, 1>},
         };
         static const Tune tune = read_tune();
         const Variant &v = kVariants[tune.variant];

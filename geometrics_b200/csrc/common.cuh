@@ -43,6 +43,35 @@ __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c)
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
     return r;
 }
+// Same operations as `asm volatile`: the compiler keeps volatile asm statements in program order, which
+// lets a kernel hand-schedule its packed-FP32 stream (dependent ops spaced >= the pipe latency apart).
+__device__ __forceinline__ u64 add2v(u64 a, u64 b)
+{
+    u64 r;
+    asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64 mul2v(u64 a, u64 b)
+{
+    u64 r;
+    asm volatile("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64 fma2v(u64 a, u64 b, u64 c)
+{
+    u64 r;
+    asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+// 4-byte asynchronous global -> shared copy (LDGSTS) and its group fence.
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // 3-input minimum (FMNMX3).  NaN operands are ignored unless all are NaN.
 __device__ __forceinline__ float min3(float a, float b, float c)
 {

@@ -85,7 +85,7 @@ __global__ void csr_fill_kernel(int V, const float *__restrict__ adj, long long 
 // ------------------------------------------------------------------------------------------
 // feature GEMM  S = X (M,K) . W (K,N), columns < ksplit -> T (M, ldt), columns >= ksplit -> Y + bias
 // ------------------------------------------------------------------------------------------
-constexpr int BM = 128, BN = 64, BK = 16, GT = 128;
+constexpr int BN = 64, BK = 16, GT = 128, APAD = 4;
 
 struct GemmArgs {
     const float *X;     // (M, K) row-major
@@ -96,26 +96,31 @@ struct GemmArgs {
     int M, K, N, ksplit, ldt, relu;
 };
 
-template <bool VEC>
+// BMT x 64 output tile per 128-thread CTA (BMT = 128: 8x8 outputs per thread; 64: 4x8, used when the
+// 128-row grid would not fill the GPU).  Thread (ty, tx) owns rows {ty*4..+3} (+64) and columns
+// {tx*4..+3} and {32+tx*4..+3}: every LDS.128 of a warp covers one contiguous 64/128-byte span, so
+// shared-memory reads are conflict-free (4 wavefronts per k-step per warp for 32 FFMA2).
+template <int BMT, bool VEC>
 __global__ void __launch_bounds__(GT, 3) gemm_kernel(const GemmArgs g)
 {
-    __shared__ __align__(16) float2 As[2][BK][BM];  // k-major, duplicated {v,v}
+    constexpr int RH = BMT / 64;  // row halves per thread (1 or 2)
+    constexpr int RT = 4 * RH;    // rows per thread
+    constexpr int AL = BMT / 32;  // A-tile float4 loads per thread
+    __shared__ __align__(16) float As[2][BK][BMT + APAD];  // k-major
     __shared__ __align__(16) float Bs[2][BK][BN];
 
     const int tid = threadIdx.x;
-    const int ty = tid >> 3, tx = tid & 7;  // 16 x 8 thread grid, 8x8 outputs each
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int ty = tid >> 3, tx = tid & 7;
+    const int m0 = blockIdx.x * BMT, n0 = blockIdx.y * BN;
 
-    // global -> register staging assignments
-    //   A tile 128 x 16: thread loads rows (tid>>2) + 32*i, i<4, k-offset (tid&3)*4 .. +3
-    //   B tile 16 x 64 : thread loads k = (tid>>4) + 8*i, i<2, cols (tid&15)*4 .. +3
+    // global -> register staging: A rows (tid>>2) + 32*i with k-offset (tid&3)*4; B k = (tid>>4) + 8*i, cols (tid&15)*4
     const int a_row = tid >> 2, a_k = (tid & 3) * 4;
     const int b_k = tid >> 4, b_n = (tid & 15) * 4;
-    float4 ra[4], rb[2];
+    float4 ra[AL], rb[2];
 
     auto load_tiles = [&](int k0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < AL; ++i) {
             const int r = m0 + a_row + 32 * i, k = k0 + a_k;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (r < g.M) {
@@ -151,20 +156,20 @@ __global__ void __launch_bounds__(GT, 3) gemm_kernel(const GemmArgs g)
     };
     auto store_tiles = [&](int buf) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < AL; ++i) {
             const int r = a_row + 32 * i;
-            As[buf][a_k + 0][r] = make_float2(ra[i].x, ra[i].x);
-            As[buf][a_k + 1][r] = make_float2(ra[i].y, ra[i].y);
-            As[buf][a_k + 2][r] = make_float2(ra[i].z, ra[i].z);
-            As[buf][a_k + 3][r] = make_float2(ra[i].w, ra[i].w);
+            As[buf][a_k + 0][r] = ra[i].x;
+            As[buf][a_k + 1][r] = ra[i].y;
+            As[buf][a_k + 2][r] = ra[i].z;
+            As[buf][a_k + 3][r] = ra[i].w;
         }
 #pragma unroll
         for (int i = 0; i < 2; ++i) *reinterpret_cast<float4 *>(&Bs[buf][b_k + 8 * i][b_n]) = rb[i];
     };
 
-    u64 acc[8][4];
+    u64 acc[RT][4];  // [row][column pair]: pairs (0,1),(2,3) of the first column group, then of the second
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < RT; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0ull;
 
@@ -177,18 +182,21 @@ __global__ void __launch_bounds__(GT, 3) gemm_kernel(const GemmArgs g)
         if (kt + 1 < nk) load_tiles((kt + 1) * BK);
 #pragma unroll
         for (int k = 0; k < BK; ++k) {
-            const ulonglong2 a01 = *reinterpret_cast<const ulonglong2 *>(&As[buf][k][ty * 8 + 0]);
-            const ulonglong2 a23 = *reinterpret_cast<const ulonglong2 *>(&As[buf][k][ty * 8 + 2]);
-            const ulonglong2 a45 = *reinterpret_cast<const ulonglong2 *>(&As[buf][k][ty * 8 + 4]);
-            const ulonglong2 a67 = *reinterpret_cast<const ulonglong2 *>(&As[buf][k][ty * 8 + 6]);
-            const ulonglong2 b03 = *reinterpret_cast<const ulonglong2 *>(&Bs[buf][k][tx * 8 + 0]);
-            const ulonglong2 b47 = *reinterpret_cast<const ulonglong2 *>(&Bs[buf][k][tx * 8 + 4]);
-            const u64 a[8] = {a01.x, a01.y, a23.x, a23.y, a45.x, a45.y, a67.x, a67.y};
-            const u64 b[4] = {b03.x, b03.y, b47.x, b47.y};
+            float av[RT];
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int h = 0; h < RH; ++h) {
+                const float4 a4 = *reinterpret_cast<const float4 *>(&As[buf][k][h * 64 + ty * 4]);
+                av[h * 4 + 0] = a4.x, av[h * 4 + 1] = a4.y, av[h * 4 + 2] = a4.z, av[h * 4 + 3] = a4.w;
+            }
+            const ulonglong2 b0 = *reinterpret_cast<const ulonglong2 *>(&Bs[buf][k][tx * 4]);
+            const ulonglong2 b1 = *reinterpret_cast<const ulonglong2 *>(&Bs[buf][k][32 + tx * 4]);
+            const u64 b[4] = {b0.x, b0.y, b1.x, b1.y};
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fma2(a[i], b[j], acc[i][j]);
+            for (int i = 0; i < RT; ++i) {
+                const u64 a2 = pack2(av[i], av[i]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma2(a2, b[j], acc[i][j]);
+            }
         }
         if (kt + 1 < nk) {
             store_tiles(buf ^ 1);
@@ -198,8 +206,8 @@ __global__ void __launch_bounds__(GT, 3) gemm_kernel(const GemmArgs g)
 
     // epilogue
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int r = m0 + ty * 8 + i;
+    for (int i = 0; i < RT; ++i) {
+        const int r = m0 + (i >> 2) * 64 + ty * 4 + (i & 3);
         if (r >= g.M) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -207,7 +215,7 @@ __global__ void __launch_bounds__(GT, 3) gemm_kernel(const GemmArgs g)
             unpack2(acc[i][j], v[0], v[1]);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const int c = n0 + tx * 8 + j * 2 + h;
+                const int c = n0 + (j >> 1) * 32 + tx * 4 + (j & 1) * 2 + h;
                 if (c >= g.N) continue;
                 if (c < g.ksplit) {
                     g.T[(size_t)r * g.ldt + c] = v[h];
@@ -376,12 +384,25 @@ extern "C" int geom_zeron_gcn_fwd(int b, int V, int in_features, int out_feature
         if (out_features <= kSkinnyMaxN) {
             skinny_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(g);
         } else {
-            dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((out_features + BN - 1) / BN));
             const bool vec = (in_features % 4 == 0) && (out_features % 4 == 0) && (((uintptr_t)X | (uintptr_t)W) & 15u) == 0;
-            if (vec)
-                gemm_kernel<true><<<grid, GT, 0, st>>>(g);
-            else
-                gemm_kernel<false><<<grid, GT, 0, st>>>(g);
+            const unsigned ny = (unsigned)((out_features + BN - 1) / BN);
+            int dev = 0, sms = 148;
+            if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            // 128-row tiles when they give the GPU at least ~2 waves of CTAs (3 resident per SM), else 64-row tiles
+            const bool big = ((M + 127) / 128) * (long long)ny >= 6LL * sms;
+            if (big) {
+                dim3 grid((unsigned)((M + 127) / 128), ny);
+                if (vec)
+                    gemm_kernel<128, true><<<grid, GT, 0, st>>>(g);
+                else
+                    gemm_kernel<128, false><<<grid, GT, 0, st>>>(g);
+            } else {
+                dim3 grid((unsigned)((M + 63) / 64), ny);
+                if (vec)
+                    gemm_kernel<64, true><<<grid, GT, 0, st>>>(g);
+                else
+                    gemm_kernel<64, false><<<grid, GT, 0, st>>>(g);
+            }
         }
     }
     cudaError_t e = cudaGetLastError();

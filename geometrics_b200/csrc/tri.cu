@@ -72,6 +72,20 @@ __device__ __forceinline__ V3 fma3(V3 d, float t, V3 s)
     return v3(__fmaf_rn(d.x, t, s.x), __fmaf_rn(d.y, t, s.y), __fmaf_rn(d.z, t, s.z));
 }
 
+// if (c) out = d * t + s, as predicated FFMAs (ptxas folds the bool -> predicate round trip).
+__device__ __forceinline__ void pfma1(float &out, bool c, float d, float t, float s)
+{
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %4, 0;\n\t@q fma.rn.f32 %0, %1, %2, %3;\n\t}"
+        : "+f"(out)
+        : "f"(d), "f"(t), "f"(s), "r"((int)c));
+}
+__device__ __forceinline__ void pfma3(V3 &out, bool c, V3 d, float t, V3 s)
+{
+    pfma1(out.x, c, d.x, t, s.x);
+    pfma1(out.y, c, d.y, t, s.y);
+    pfma1(out.z, c, d.z, t, s.z);
+}
+
 // Operand range in which Markstein's correction is exact: every intermediate stays a normal number.
 constexpr float kDivLo = 1.0842021724855044e-19f;  // 2^-63
 constexpr float kDivHi = 9.2233720368547758e+18f;  // 2^63
@@ -187,22 +201,21 @@ __device__ __forceinline__ float tri_pair_fast(V3 p, const TriRegs &t)
     const bool c1 = (uca > 1.0f) && (uab < 0.0f);
     const bool c2 = (uab > 1.0f) && (ubc < 0.0f);
     const bool c3 = (ubc > 1.0f) && (uca < 0.0f);
-    const bool vtx = c1 || c2 || c3;
     const bool e4 = in_range(uab) && !(dot_s1(t.xab, pA) > 0.0f);
     const bool e5 = in_range(ubc) && !(dot_s1(t.xbc, pB) > 0.0f);
     const bool e6 = in_range(uca) && !(dot_s1(t.xca, pC) > 0.0f);
-    // cascade order: vertex A, B, C, edge AB, BC, CA(sic), plane
-    const bool selA = c1 || (!vtx && e4);
-    const bool selB = (!c1 && c2) || (!vtx && !e4 && e5);
-    const bool plane = !vtx && !e4 && !e5 && !e6;
-    // vertex regions are the edge form with parameter 0: S + D*0 == S (D is finite)
-    const float tt = vtx ? 0.0f : (e4 ? uab : (e5 ? ubc : uca));
-    const V3 S = sel3(selA, t.A, sel3(selB, t.B, t.C));
-    const V3 D = sel3(selB, t.BC, t.AB);  // the CA region uses AB's direction (tri_distance.cu:180)
-    const V3 p2e = fma3(D, tt, S);
+    // The cascade (vertex A, B, C, edge AB, BC, CA(sic), plane) as predicated overwrites in reverse
+    // priority order: no select chains, no predicate algebra; all arithmetic stays on the FMA pipe.
+    // Vertex regions are the edge form with parameter 0: S + D*0 == S (D is finite).
     const float dist = dot_s1(pA, t.nn);
-    const V3 p2p = v3(__fmaf_rn(-t.nn.x, dist, p.x), __fmaf_rn(-t.nn.y, dist, p.y), __fmaf_rn(-t.nn.z, dist, p.z));
-    const V3 df = vsub(p, sel3(plane, p2p, p2e));
+    V3 p2 = v3(__fmaf_rn(-t.nn.x, dist, p.x), __fmaf_rn(-t.nn.y, dist, p.y), __fmaf_rn(-t.nn.z, dist, p.z));
+    pfma3(p2, e6, t.AB, uca, t.C);  // the CA region uses AB's direction (tri_distance.cu:180)
+    pfma3(p2, e5, t.BC, ubc, t.B);
+    pfma3(p2, e4, t.AB, uab, t.A);
+    pfma3(p2, c3, t.AB, 0.0f, t.C);
+    pfma3(p2, c2, t.BC, 0.0f, t.B);
+    pfma3(p2, c1, t.AB, 0.0f, t.A);
+    const V3 df = vsub(p, p2);
     return dot_s1(df, df);
 }
 

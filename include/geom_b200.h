@@ -83,6 +83,20 @@ GEOM_API int geom_chamfer_fwd(int b, int n, const float *xyz1, int m, const floa
                      float *dist1, int *idx1, float *dist2, int *idx2,
                      void *workspace, size_t workspace_bytes, unsigned flags, geom_stream_t stream);
 
+/* Host-buffer form of geom_chamfer_fwd: every pointer is HOST memory (pinned memory gives full
+ * copy/compute overlap; pageable memory works, staged by the driver).  The batch is cut into `chunks`
+ * slices (<= 8; 0 = default 4): slice k+1 is copied to the device while slice k is searched and slice
+ * k-1's results are copied back, on three internal streams.  Synchronous: returns when all results
+ * are in host memory.  h_dist1 / h_dist2 may be NULL.  A geom_host_ctx owns the streams, events and a
+ * device arena reused across calls; create one per calling thread, on the device it should use.
+ * This is the end-to-end path bench.py reports as "e2e". */
+typedef struct geom_host_ctx geom_host_ctx;
+GEOM_API int geom_host_ctx_create(geom_host_ctx **out);
+GEOM_API int geom_host_ctx_destroy(geom_host_ctx *ctx);
+GEOM_API int geom_chamfer_fwd_host(geom_host_ctx *ctx, int b, int n, const float *h_xyz1, int m,
+                          const float *h_xyz2, float *h_dist1, int *h_idx1, float *h_dist2, int *h_idx2,
+                          int chunks, unsigned flags);
+
 /* ---------------------------------------------------------------------------------------------
  * Chamfer loss on the indices (forward sums and backward scatter).
  * Replaces the torch chain after chamfer_dist() in utils.py:402-417 (batch_point_to_point) and

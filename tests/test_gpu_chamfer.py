@@ -165,3 +165,26 @@ def _first_min_equal(dd, idx):
     mn = dd.min(-1, keepdim=True).values
     first = (dd == mn).int().argmax(-1)
     return torch.equal(first.int(), idx)
+
+
+@pytest.mark.parametrize("pinned", [True, False])
+def test_host_buffer_entry(oracle, cuda, pinned):
+    """geom_chamfer_fwd_host: host tensors in, host indices (and distances) out, chunk-pipelined."""
+    import geometrics_b200 as g
+
+    x1, x2 = chamfer_inputs("random", 5, 1500, 1030, 77)
+    want = oracle.chamfer_fwd(x1.numpy(), x2.numpy())
+    bufs = [torch.empty(5, 1500, dtype=torch.int32), torch.empty(5, 1030, dtype=torch.int32),
+            torch.empty(5, 1500), torch.empty(5, 1030)]
+    if pinned:
+        x1, x2 = x1.pin_memory(), x2.pin_memory()
+        bufs = [t.pin_memory() for t in bufs]
+    for chunks in (1, 2, 4, 8):
+        for t in bufs:
+            t.fill_(-1)
+        g.chamfer_forward_host(x1, x2, bufs[0], bufs[1], device=cuda, chunks=chunks, dist1_out=bufs[2], dist2_out=bufs[3])
+        assert (bufs[0].numpy() == want[1]).all() and (bufs[1].numpy() == want[3]).all(), chunks
+        assert_same_f32(bufs[2].numpy(), want[0])
+        assert_same_f32(bufs[3].numpy(), want[2])
+    with pytest.raises(RuntimeError):
+        g.chamfer_forward_host(x1.to(cuda), x2, bufs[0], bufs[1])
