@@ -282,11 +282,11 @@ def run_product(args):
     hi2 = torch.empty(B, M_PTS, dtype=torch.int32).pin_memory()
     e2e_steps = max(3, min(args.steps, 30))
     for _ in range(2):
-        g.chamfer_forward_host(hx1, hx2, hi1, hi2, device=dev)
+        g.chamfer_forward_host(hx1, hx2, hi1, hi2, device=dev, chunks=args.e2e_chunks)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        g.chamfer_forward_host(hx1, hx2, hi1, hi2, device=dev)  # returns after the D2H copy completed
+        g.chamfer_forward_host(hx1, hx2, hi1, hi2, device=dev, chunks=args.e2e_chunks)  # returns after the D2H copy completed
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
 
@@ -318,7 +318,7 @@ def run_product(args):
             "clocks": clocks,
             "e2e": {"value": pairs_step / e2e_s, "unit": UNIT, "h2d_bytes_per_step": hx1.numel() * 4 + hx2.numel() * 4,
                     "d2h_bytes_per_step": hi1.numel() * 4 + hi2.numel() * 4, "ms_per_step": e2e_s * 1e3,
-                    "api": "geom_chamfer_fwd_host via geometrics_b200.chamfer_forward_host (pinned host in/out, 4 batch chunks pipelined)", "steps": e2e_steps},
+                    "api": "geom_chamfer_fwd_host via geometrics_b200.chamfer_forward_host (pinned host in/out, batch chunks pipelined)", "chunks": args.e2e_chunks, "steps": e2e_steps},
             "gpu_launches": launches,
             "kernels": {k_: {"ms_per_launch": v[0] / v[1], "launches": v[1], "share_of_step": v[0] / args.steps / ms_step}
                         for k_, v in kern.items()},
@@ -344,6 +344,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-chunks", type=int, default=4, help="batch chunks pipelined by geom_chamfer_fwd_host")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "product" else args.warmup
     if args.impl == "reference":

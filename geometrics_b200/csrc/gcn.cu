@@ -314,10 +314,42 @@ spmm_bwd_kernel(int rows, int V, int N, int ksplit, const int *__restrict__ t_ro
     }
 }
 
+// Plain CSR SpMM over every feature column: Y[b,i,c] = sum_j val(i,j) X[b,j,c]  (Laplacian
+// regulariser, utils.py:654-662).  One thread per output element.
+__global__ void __launch_bounds__(256)
+spmm_plain_kernel(long long total, int V, int C, const int *__restrict__ row_ptr, const int *__restrict__ col_idx,
+                  const float *__restrict__ val, const float *__restrict__ X, float *__restrict__ Y)
+{
+    const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (t >= total) return;
+    const int c = (int)(t % C);
+    const long long row = t / C;
+    const int i = (int)(row % V);
+    const float *Xb = X + (row - i) * C;
+    float acc = 0.f;
+    for (int p = row_ptr[i]; p < row_ptr[i + 1]; ++p) acc = fmaf(val[p], Xb[(size_t)col_idx[p] * C + c], acc);
+    Y[t] = acc;
+}
+
 }  // namespace gcn
 }  // namespace geom
 
 using namespace geom;
+
+extern "C" int geom_csr_spmm(int b, int V, int C, const int *row_ptr, const int *col_idx, const float *val,
+                             const float *X, float *Y, geom_stream_t stream)
+{
+    if (b < 0 || V < 0 || C < 0) return GEOM_ERR_INVALID_ARG;
+    const long long total = (long long)b * V * C;
+    if (total == 0) return GEOM_OK;
+    if (!row_ptr || !col_idx || !val || !X || !Y) return GEOM_ERR_INVALID_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    {
+        prof::Scope ps(st, prof::kMisc2);
+        gcn::spmm_plain_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(total, V, C, row_ptr, col_idx, val, X, Y);
+    }
+    return status_from_cuda(cudaGetLastError());
+}
 
 extern "C" int geom_csr_count(int V, const float *adj, int transpose, int *row_cnt, int *row_ptr,
                               geom_stream_t stream)

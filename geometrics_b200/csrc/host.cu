@@ -81,7 +81,20 @@ extern "C" int geom_chamfer_fwd_host(geom_host_ctx *c, int b, int n, const float
     if (chunks < 1) chunks = 4;
     if (chunks > geom_host_ctx::kMaxChunks) chunks = geom_host_ctx::kMaxChunks;
     if (chunks > b) chunks = b;
-    const int per = (b + chunks - 1) / chunks;
+    // Slice boundaries: small first and last slices (only the first copy-in and the last copy-out are
+    // exposed), the rest split evenly.  lo[k]..lo[k+1] is slice k.
+    int lo_of[geom_host_ctx::kMaxChunks + 1];
+    {
+        const int edge = (chunks >= 3) ? ((b / 8 > 0) ? b / 8 : 1) : 0;
+        const int inner = chunks - (edge ? 2 : 0), rest = b - 2 * edge;
+        int pos = 0, k = 0;
+        lo_of[k++] = 0;
+        if (edge) lo_of[k++] = (pos += edge);
+        for (int i = 0; i < inner; ++i) lo_of[k++] = (pos += rest / inner + (i < rest % inner ? 1 : 0));
+        if (edge) lo_of[k++] = (pos += edge);
+    }
+    int per = 0;
+    for (int k = 0; k < chunks; ++k) per = (lo_of[k + 1] - lo_of[k] > per) ? lo_of[k + 1] - lo_of[k] : per;
 
     // arena layout: xyz1 | xyz2 | idx1 | idx2 | dist1 | dist2 | one search workspace per chunk
     const size_t s_x1 = align_up(sizeof(float) * 3 * (size_t)b * n, 256), s_x2 = align_up(sizeof(float) * 3 * (size_t)b * m, 256);
@@ -98,8 +111,8 @@ extern "C" int geom_chamfer_fwd_host(geom_host_ctx *c, int b, int n, const float
     char *d_ws = base + s_x1 + s_x2 + s_i1 + s_i2 + s_d1 + s_d2;
 
     for (int k = 0; k < chunks; ++k) {
-        const int lo = k * per, hi = (lo + per < b) ? lo + per : b;
-        if (lo >= hi) break;
+        const int lo = lo_of[k], hi = lo_of[k + 1];
+        if (lo >= hi) continue;
         const size_t o1 = (size_t)lo * n, o2 = (size_t)lo * m, c1 = (size_t)(hi - lo) * n, c2 = (size_t)(hi - lo) * m;
         if (c1) e = cudaMemcpyAsync(d_x1 + o1 * 3, h_xyz1 + o1 * 3, sizeof(float) * 3 * c1, cudaMemcpyHostToDevice, c->h2d);
         if (e == cudaSuccess && c2)

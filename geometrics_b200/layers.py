@@ -66,6 +66,47 @@ def csr_from_dense(adj: torch.Tensor) -> CsrAdjacency:
     return c
 
 
+class CsrMatmulFunction(torch.autograd.Function):
+    """Y = A X for the cached CSR of a dense (V,V) matrix and X (B,V,C); backward uses the CSR of A^T."""
+
+    @staticmethod
+    def forward(ctx, x, csr):
+        L = _lib.lib()
+        xc = x.detach().contiguous()
+        b, v, c = xc.shape
+        y = torch.empty_like(xc)
+        with torch.cuda.device(xc.device):
+            _lib.check(L.geom_csr_spmm(b, v, c, csr.row_ptr.data_ptr(), csr.col_idx.data_ptr(), csr.val.data_ptr(),
+                                       xc.data_ptr(), y.data_ptr(), _lib.current_stream_ptr(xc.device)), "geom_csr_spmm")
+        ctx.csr = csr
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        L = _lib.lib()
+        csr = ctx.csr
+        dy = dy.contiguous()
+        b, v, c = dy.shape
+        dx = torch.empty_like(dy)
+        with torch.cuda.device(dy.device):
+            _lib.check(L.geom_csr_spmm(b, v, c, csr.t_row_ptr.data_ptr(), csr.t_col_idx.data_ptr(), csr.t_val.data_ptr(),
+                                       dy.data_ptr(), dx.data_ptr(), _lib.current_stream_ptr(dy.device)), "geom_csr_spmm")
+        return dx, None
+
+
+def csr_matmul(adj, x):
+    """``torch.matmul(adj, x)`` for a dense (V,V) ``adj`` (converted once to CSR) and x (B,V,C) or (V,C)."""
+    _lib.require_cuda_f32("x", x)
+    squeeze = x.dim() == 2
+    if squeeze:
+        x = x.unsqueeze(0)
+    csr = adj if isinstance(adj, CsrAdjacency) else csr_from_dense(adj)
+    if csr.V != x.shape[1]:
+        raise ValueError(f"matrix is {csr.V}x{csr.V} but x has {x.shape[1]} rows")
+    y = CsrMatmulFunction.apply(x, csr)
+    return y.squeeze(0) if squeeze else y
+
+
 # ------------------------------------------------------------------------------------------------
 # the fused layer
 # ------------------------------------------------------------------------------------------------

@@ -325,3 +325,36 @@ def batch_point_to_surface(pred_vert, adj_info, gt_points, num=1000, f1=False, g
     if f1:
         return loss, _f_score(gt, pred_points.detach(), id_p, id_g, num)
     return loss
+
+
+# ------------------------------------------------------------------------------------------------
+# regularisers
+# ------------------------------------------------------------------------------------------------
+def batch_calc_edge(verts, info):
+    """Mean squared edge length over the three edges of every face (utils.py:636-651); plain torch."""
+    faces = info["faces"]
+    p1 = torch.index_select(verts, 1, faces[:, 0])
+    p2 = torch.index_select(verts, 1, faces[:, 1])
+    p3 = torch.index_select(verts, 1, faces[:, 2])
+    e1, e2, e3 = p2 - p1, p3 - p1, p2 - p3
+    return (torch.sum(e1 ** 2, -1).mean() + torch.sum(e2 ** 2, -1).mean() + torch.sum(e3 ** 2, -1).mean()) / 3.
+
+
+_degree_cache: dict = {}
+
+
+def batch_get_lap_info(positions, adj_info):
+    """Uniform Laplacian coordinates (utils.py:654-662): positions minus the mean of the neighbours.
+    The reference's dense ``adj_orig @ positions`` (called six times per step, GEOMetrics.py:156-160)
+    becomes a CSR SpMM over the three coordinate columns."""
+    from .layers import csr_matmul
+
+    orig = adj_info["adj_orig"]
+    key = (orig.data_ptr(), orig._version, orig.shape[0])
+    scaler = _degree_cache.get(key)
+    if scaler is None:
+        if len(_degree_cache) > 16:
+            _degree_cache.clear()
+        scaler = _degree_cache[key] = (1. / (torch.sum(orig, dim=1) - 1)).view(-1, 1)
+    neighbor_sum = (csr_matmul(orig, positions) - positions) * scaler
+    return positions - neighbor_sum

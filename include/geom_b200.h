@@ -197,6 +197,10 @@ GEOM_API int geom_csr_count(int V, const float *adj, int transpose, int *row_cnt
                    geom_stream_t stream);
 GEOM_API int geom_csr_fill(int V, const float *adj, int transpose, const int *row_ptr, int *col_idx,
                   float *val, geom_stream_t stream);
+/* Y (B,V,C) = A . X (B,V,C) for a CSR matrix A (V,V) shared by the batch: the dense
+ * `torch.matmul(adj_orig, positions)` of the Laplacian regulariser (utils.py:654-662). */
+GEOM_API int geom_csr_spmm(int b, int V, int C, const int *row_ptr, const int *col_idx, const float *val,
+                  const float *X, float *Y, geom_stream_t stream);
 GEOM_API size_t geom_zeron_gcn_workspace_bytes(int b, int V, int ksplit);
 GEOM_API int geom_zeron_gcn_fwd(int b, int V, int in_features, int out_features, int ksplit, const float *X,
                        const float *W, const float *bias, const int *row_ptr, const int *col_idx,

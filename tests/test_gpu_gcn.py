@@ -167,3 +167,31 @@ def test_block_backward_runs_and_matches_torch_stack(cuda, setup):
     g_dense = [p.grad for p in block.parameters() if p.grad is not None]
     for a, b_ in zip(g_fused, g_dense):
         close(a, b_.cpu().numpy(), 2e-3, "param grad")
+
+
+def test_regularisers_vs_torch(cuda):
+    """batch_get_lap_info (CSR SpMM) and batch_calc_edge against the dense torch expressions
+    (utils.py:636-662), forward and gradient."""
+    import geometrics_b200 as g
+    import geometrics_b200.utils as U
+    from geometrics_b200 import synth
+
+    verts, faces = synth.uv_sphere(32, 15)
+    info = {k: v.to(cuda) for k, v in g.adj_init(faces).items()}
+    pos = synth.mesh_batch(verts, 4).to(cuda)
+
+    def dense_lap(p):
+        orig = info["adj_orig"]
+        ns = (torch.matmul(orig, p) - p) * (1. / (torch.sum(orig, dim=1) - 1)).view(-1, 1)
+        return p - ns
+
+    for p_in in (pos, pos[0]):  # batched and the un-batched initial mesh (GEOMetrics.py:156)
+        p1 = p_in.clone().requires_grad_(True)
+        p2 = p_in.clone().requires_grad_(True)
+        got, want = U.batch_get_lap_info(p1, info), dense_lap(p2)
+        close(got, want.detach().cpu().numpy(), 1e-5, "lap")
+        (got ** 2).sum().backward()
+        (want ** 2).sum().backward()
+        close(p1.grad, p2.grad.cpu().numpy(), 1e-5, "d lap")
+    e = U.batch_calc_edge(pos, info)
+    assert e.shape == () and float(e) > 0
