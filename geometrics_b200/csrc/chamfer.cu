@@ -31,7 +31,6 @@ namespace chamfer {
 
 constexpr int kWarps = 4;
 constexpr int kThreads = 32 * kWarps;
-constexpr int kMaxTileCols = 256;
 constexpr int kGroupCols = 8;           // tag granularity of the row keys (two 4-column steps)
 constexpr int kRefTile = 512;           // the reference kernel's smem tile (chamfer_distance.cu:15)
 

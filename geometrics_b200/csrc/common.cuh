@@ -31,6 +31,12 @@ __device__ __forceinline__ u64 add2(u64 a, u64 b)
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
+__device__ __forceinline__ u64 sub2(u64 a, u64 b)
+{
+    u64 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
 __device__ __forceinline__ u64 mul2(u64 a, u64 b)
 {
     u64 r;
