@@ -162,6 +162,45 @@ __global__ void __launch_bounds__(kThreads, MINB) twoway_kernel(const TwoWayArgs
                 float nb[R];
 #pragma unroll
                 for (int r = 0; r < R; ++r) nb[r] = best[r];
+                if (ORD == 2) {
+                    // two columns per step: half the live registers of the 4-column step (more warps/SM)
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        const int col = g * kGroupCols + s * 2;
+                        const ulonglong2 xa = *reinterpret_cast<const ulonglong2 *>(&sq[0][col]);
+                        const ulonglong2 ya = *reinterpret_cast<const ulonglong2 *>(&sq[1][col]);
+                        const ulonglong2 za = *reinterpret_cast<const ulonglong2 *>(&sq[2][col]);
+                        const u64 qx[2] = {xa.x, xa.y}, qy[2] = {ya.x, ya.y}, qz[2] = {za.x, za.y};
+                        float d[2][R];
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+#pragma unroll
+                            for (int i = 0; i < R / 2; ++i) {
+                                const u64 dx = add2(qx[c], nx[i]);
+                                const u64 dy = add2(qy[c], ny[i]);
+                                const u64 dz = add2(qz[c], nz[i]);
+                                const u64 dd = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
+                                unpack2(dd, d[c][2 * i], d[c][2 * i + 1]);
+                            }
+                        }
+#pragma unroll
+                        for (int r = 0; r < R; ++r) nb[r] = min3(nb[r], d[0][r], d[1][r]);
+                        unsigned cv[2];
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            float cm = min3(d[c][0], d[c][1], d[c][2]);
+                            if (R == 4) {
+                                cm = fminf(cm, d[c][3]);
+                            } else {
+#pragma unroll
+                                for (int r = 3; r + 1 < R; r += 2) cm = min3(cm, d[c][r], d[c][r + 1]);
+                                cm = fminf(cm, d[c][R - 1]);
+                            }
+                            cv[c] = __reduce_min_sync(0xffffffffu, __float_as_uint(cm));
+                        }
+                        if (lane == 0) *reinterpret_cast<uint2 *>(&scol[col]) = make_uint2(cv[0], cv[1]);
+                    }
+                } else {
 #pragma unroll
                 for (int s = 0; s < 2; ++s) {
                     const int col = g * kGroupCols + s * 4;
@@ -240,6 +279,7 @@ __global__ void __launch_bounds__(kThreads, MINB) twoway_kernel(const TwoWayArgs
                         cv[c] = __reduce_min_sync(0xffffffffu, __float_as_uint(cm));
                     }
                     if (lane == 0) *reinterpret_cast<uint4 *>(&scol[col]) = make_uint4(cv[0], cv[1], cv[2], cv[3]);
+                }
                 }
                 const unsigned gid = gid0 + (unsigned)g;
 #pragma unroll
@@ -448,7 +488,7 @@ static Tune read_tune()
     if (const char *e = getenv("GEOM_CHAMFER_TUNE")) {
         int v = 0, s = 0, tc = 0;
         const int got = sscanf(e, "%d,%d,%d", &v, &s, &tc);
-        if (got >= 1 && v >= 0 && v < 5) t.variant = v;
+        if (got >= 1 && v >= 0 && v < 8) t.variant = v;
         if (got >= 2 && s >= 1) t.strip = s;
         if (got >= 3 && tc >= 32) t.tile_cols = tc;
     }
@@ -509,6 +549,9 @@ extern "C" int geom_chamfer_fwd(int b, int n, const float *xyz1, int m, const fl
             {8, 4, 128, twoway_kernel<8, 4, 128, 0>},
             {8, 4, 128, twoway_kernel<8, 4, 128, 1>},
             {8, 3, 256, twoway_kernel<8, 3, 256, 1>},
+            {8, 5, 256, twoway_kernel<8, 5, 256, 2>},
+            {8, 6, 128, twoway_kernel<8, 6, 128, 2>},
+            {8, 4, 256, twoway_kernel<8, 4, 256, 2>},
         };
         static const Tune tune = read_tune();
         const Variant &v = kVariants[tune.variant];

@@ -171,7 +171,8 @@ def main():
     if args.sync_bn and world > 1:
         mods = [nn.SyncBatchNorm.convert_sync_batchnorm(m) for m in mods]
     if world > 1:
-        mods = [nn.parallel.DistributedDataParallel(m, device_ids=[local]) for m in mods]
+        # bn14 exists in the reference block but is never used in forward (models.py:235): unused parameters
+        mods = [nn.parallel.DistributedDataParallel(m, device_ids=[local], find_unused_parameters=True) for m in mods]
     encoders, blocks = mods[:3], mods[3:]
     params = [p for m in mods for p in m.parameters()]
     opt = torch.optim.Adam(params, lr=1e-4)
