@@ -17,6 +17,7 @@ GEOM_ABI_VERSION = 1
 GEOM_FLAG_NONE = 0
 GEOM_FLAG_EXACT_TAIL = 1
 GEOM_FLAG_ONEWAY = 2
+GEOM_FLAG_TENSOR = 4
 
 # every symbol include/geom_b200.h declares: name -> (restype, argtypes)
 _vp, _i, _u, _sz = C.c_void_p, C.c_int, C.c_uint, C.c_size_t

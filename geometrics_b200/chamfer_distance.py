@@ -15,7 +15,7 @@ from . import _lib
 
 
 def chamfer_forward(xyz1: torch.Tensor, xyz2: torch.Tensor, *, exact_tail: bool = False,
-                    oneway: bool = False, want_dist: bool = True):
+                    oneway: bool = False, want_dist: bool = True, tensor: bool = False):
     """-> (dist1, idx1, dist2, idx2); squared distances are fp32 (B,n)/(B,m) or None."""
     _lib.require_cuda_f32("xyz1", xyz1, 3)
     _lib.require_cuda_f32("xyz2", xyz2, 3)
@@ -35,8 +35,9 @@ def chamfer_forward(xyz1: torch.Tensor, xyz2: torch.Tensor, *, exact_tail: bool 
         dist1 = torch.empty((b, n), dtype=torch.float32, device=dev) if want_dist else None
         dist2 = torch.empty((b, m), dtype=torch.float32, device=dev) if want_dist else None
         ws_bytes = L.geom_chamfer_workspace_bytes(b, n, m)
-        ws = torch.empty((max(ws_bytes, 8) + 7) // 8, dtype=torch.int64, device=dev)
-        flags = (_lib.GEOM_FLAG_EXACT_TAIL if exact_tail else 0) | (_lib.GEOM_FLAG_ONEWAY if oneway else 0)
+        ws = torch.empty((max(ws_bytes, 16) + 15) // 16 * 2, dtype=torch.int64, device=dev)
+        flags = (_lib.GEOM_FLAG_EXACT_TAIL if exact_tail else 0) | (_lib.GEOM_FLAG_ONEWAY if oneway else 0) \
+            | (_lib.GEOM_FLAG_TENSOR if tensor else 0)
         st = L.geom_chamfer_fwd(
             b, n, xyz1.data_ptr(), m, xyz2.data_ptr(),
             dist1.data_ptr() if want_dist else None, idx1.data_ptr(),

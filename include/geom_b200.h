@@ -50,6 +50,9 @@ typedef void *geom_stream_t; /* cudaStream_t */
 #define GEOM_FLAG_EXACT_TAIL 1u
 /* Chamfer only: use the simple one-direction-at-a-time kernel instead of the fused two-way one. */
 #define GEOM_FLAG_ONEWAY 2u
+/* Chamfer only: tensor-core filtered exact search (tcgen05 bf16 contraction as a conservative filter,
+ * exact fp32 re-evaluation of the survivors); same results, bit for bit. */
+#define GEOM_FLAG_TENSOR 4u
 
 GEOM_API int geom_abi_version(void);
 /* Static string for a status returned by any geom_* call. */

@@ -188,3 +188,48 @@ def test_host_buffer_entry(oracle, cuda, pinned):
         assert_same_f32(bufs[3].numpy(), want[2])
     with pytest.raises(RuntimeError):
         g.chamfer_forward_host(x1.to(cuda), x2, bufs[0], bufs[1])
+
+
+# ---------------------------------------------------------------------------- tensor-core filtered path
+@pytest.mark.parametrize("exact", [False, True], ids=["default", "exact_tail"])
+@pytest.mark.parametrize("case", CHAMFER_CASES, ids=_ids)
+def test_tensor_path_matches_oracle(oracle, cuda, case, exact):
+    """GEOM_FLAG_TENSOR (tcgen05 bf16 filter + exact fp32 re-evaluation) is bit-identical to the oracle."""
+    x1, x2 = chamfer_inputs(*case)
+    got = _run(x1, x2, cuda, tensor=True, exact_tail=exact)
+    want = oracle.chamfer_fwd(x1.numpy(), x2.numpy(), exact=exact)
+    for name, g_, w_ in zip(("dist1", "idx1", "dist2", "idx2"), got, want):
+        if name.startswith("dist"):
+            assert_same_f32(g_, w_, name)
+        else:
+            assert (g_ == w_).all(), f"{name}: {np.count_nonzero(g_ != w_)} of {w_.size} indices differ"
+
+
+@pytest.mark.parametrize("scale,offset", [(1.0, 0.0), (100.0, 0.0), (1e-3, 0.0), (1.0, 50.0), (1e6, 0.0)])
+def test_tensor_path_full_size_and_ranges(cuda, scale, offset):
+    """Config-2 size and other coordinate ranges (the filter margin scales with max|coord|^2): equal to
+    the brute-force kernel bit for bit; lattice / duplicate data exercise ties."""
+    from geometrics_b200 import synth
+    import geometrics_b200 as g
+
+    b = 32 if scale == 1.0 and offset == 0.0 else 4
+    for mk in (synth.random_points, lambda b_, n_, s_: synth.lattice_points(b_, n_, 64, s_)):
+        x1 = (mk(b, 10000, 41) * scale + offset).to(cuda)
+        x2 = (mk(b, 10000, 42) * scale + offset).to(cuda)
+        want = g.chamfer_forward(x1, x2)
+        got = g.chamfer_forward(x1, x2, tensor=True)
+        for a_, b_ in zip(got, want):
+            assert torch.equal(a_, b_)
+
+
+def test_tensor_path_margin(cuda, monkeypatch):
+    """The filter stays exact with its margin shrunk 8x: the shipped margin has headroom."""
+    from geometrics_b200 import synth
+    import geometrics_b200 as g
+
+    x1, x2 = synth.random_points(8, 10000, 3).to(cuda), synth.random_points(8, 10000, 4).to(cuda)
+    want = g.chamfer_forward(x1, x2)
+    monkeypatch.setenv("GEOM_TC_EPS_SCALE", "0.125")
+    got = g.chamfer_forward(x1, x2, tensor=True)
+    for a_, b_ in zip(got, want):
+        assert torch.equal(a_, b_)

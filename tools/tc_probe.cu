@@ -1,0 +1,296 @@
+// tc_probe.cu -- standalone check of the hand-written tcgen05 plumbing used by the tensor-core Chamfer
+// filter: one CTA stages a 128x16 and a 256x16 bf16 operand tile in shared memory (K-major, no
+// swizzle, canonical "interleave" layout), issues ONE tcgen05.mma (M=128, N=256, K=16, fp32
+// accumulate in TMEM), reads the accumulator back with tcgen05.ld and compares with the CPU.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o tools/tc_probe tools/tc_probe.cu && ./tools/tc_probe
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <vector>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+
+#define M_ 128
+#define N_ 256
+#define K_ 16
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version 1 (sm_100)
+    return d;                // base_offset 0, lbo_mode 0, layout_type 0 = no swizzle
+}
+
+__global__ void __launch_bounds__(128) probe(const __nv_bfloat16 *A, const __nv_bfloat16 *B, float *out, int variant)
+{
+    // operand tiles: [k-chunk (2)][row][8 bf16 = 16 B]
+    __shared__ __align__(128) uint4 sA[2][M_];
+    __shared__ __align__(128) uint4 sB[2][N_];
+    __shared__ __align__(8) unsigned long long bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(256u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar)), "r"(1u));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    // global rows are [row][16 bf16] (32 B): split each row into its two 16-byte k-chunks
+    for (int i = tid; i < M_ * 2; i += 128) sA[i & 1][i >> 1] = reinterpret_cast<const uint4 *>(A)[i];
+    for (int i = tid; i < N_ * 2; i += 128) sB[i & 1][i >> 1] = reinterpret_cast<const uint4 *>(B)[i];
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+
+    if (tid == 0) {
+        // variant 0: LBO = k-chunk plane stride, SBO = 8-row group stride (128 B); variant 1: swapped
+        const uint32_t lboA = variant == 0 ? M_ * 16 : 128, sboA = variant == 0 ? 128 : M_ * 16;
+        const uint32_t lboB = variant == 0 ? N_ * 16 : 128, sboB = variant == 0 ? 128 : N_ * 16;
+        const uint64_t da = make_desc(smem_u32(&sA[0][0]), lboA, sboA);
+        const uint64_t db = make_desc(smem_u32(&sB[0][0]), lboB, sboB);
+        // instruction descriptor: D = f32 (1<<4), A = B = bf16 (1<<7, 1<<10), K-major both, N>>3 at 17, M>>4 at 24
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_ >> 3) << 17) | ((uint32_t)(M_ >> 4) << 24);
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(0u) : "memory");
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    }
+    // wait for the MMA (phase 0)
+    {
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(smem_u32(&bar)), "r"(0u) : "memory");
+        }
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // each warp reads its 32 TMEM lanes (= rows 32*warp .. +31), 32 columns at a time
+    for (int c0 = 0; c0 < N_; c0 += 32) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int k = 0; k < 32; ++k) out[(size_t)(warp * 32 + lane) * N_ + c0 + k] = __uint_as_float(v[k]);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u));
+}
+
+// throughput: REPS back-to-back MMAs (N columns wide) then one commit; cycles per MMA
+template <int NCOLS>
+__global__ void __launch_bounds__(128) mma_rate(const __nv_bfloat16 *A, const __nv_bfloat16 *B, long long *cycles, int reps)
+{
+    __shared__ __align__(128) uint4 sA[2][M_];
+    __shared__ __align__(128) uint4 sB[2][N_];
+    __shared__ __align__(8) unsigned long long bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(256u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar)), "r"(1u));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    for (int i = tid; i < M_ * 2; i += 128) sA[i & 1][i >> 1] = reinterpret_cast<const uint4 *>(A)[i];
+    for (int i = tid; i < N_ * 2; i += 128) sB[i & 1][i >> 1] = reinterpret_cast<const uint4 *>(B)[i];
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+    long long t0 = 0, t1 = 0;
+    if (tid == 0) {
+        const uint64_t da = make_desc(smem_u32(&sA[0][0]), M_ * 16, 128);
+        const uint64_t db = make_desc(smem_u32(&sB[0][0]), N_ * 16, 128);
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NCOLS >> 3) << 17) | ((uint32_t)(M_ >> 4) << 24);
+        t0 = clock64();
+        for (int r = 0; r < reps; ++r)
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                ::"r"(tmem + (uint32_t)((r & 1) * 128 * (NCOLS <= 128))), "l"(da), "l"(db), "r"(idesc), "r"(0u) : "memory");
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    }
+    {
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(smem_u32(&bar)), "r"(0u) : "memory");
+    }
+    if (tid == 0) { t1 = clock64(); cycles[blockIdx.x] = t1 - t0; }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u));
+}
+
+// pipeline probe: 1 producer warp + 8 scanner warps, double-buffered 128-column accumulators, no real
+// scan work (WORK = number of dependent min3 per 32 loaded values), measures cycles per unit per CTA.
+__device__ __forceinline__ void mbar_wait_p(unsigned long long *bar, unsigned parity)
+{
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+template <int WORK, int NLD>
+__global__ void __launch_bounds__(288, 2) pipe_probe(const __nv_bfloat16 *A, const __nv_bfloat16 *B, long long *cycles, float *sink, int units)
+{
+    __shared__ __align__(128) uint4 sA[2][M_];
+    __shared__ __align__(128) uint4 sB[2][128];
+    __shared__ __align__(8) unsigned long long full_bar[2], empty_bar[2];
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(256u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&full_bar[i])), "r"(1u));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&empty_bar[i])), "r"(8u));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    for (int i = tid; i < M_ * 2; i += 288) sA[i & 1][i >> 1] = reinterpret_cast<const uint4 *>(A)[i];
+    for (int i = tid; i < 128 * 2; i += 288) sB[i & 1][i >> 1] = reinterpret_cast<const uint4 *>(B)[i];
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+    const long long t0 = clock64();
+    if (warp == 8) {
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(M_ >> 4) << 24);
+        const uint64_t da = make_desc(smem_u32(&sA[0][0]), M_ * 16, 128), db = make_desc(smem_u32(&sB[0][0]), 128 * 16, 128);
+        for (int gu = 0; gu < units; ++gu) {
+            if (gu >= 2) mbar_wait_p(&empty_bar[gu & 1], (uint32_t)(((gu >> 1) - 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                             ::"r"(tmem + (uint32_t)((gu & 1) * 128)), "l"(da), "l"(db), "r"(idesc), "r"(0u) : "memory");
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&full_bar[gu & 1])) : "memory");
+            }
+            __syncwarp();
+        }
+    } else {
+        const int half = warp >> 2;
+        float acc = 1e30f;
+        for (int gu = 0; gu < units; ++gu) {
+            mbar_wait_p(&full_bar[gu & 1], (uint32_t)((gu >> 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tb = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((gu & 1) * 128 + half * 64);
+            uint32_t v[2][32];
+#pragma unroll
+            for (int h = 0; h < NLD; ++h) {
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[h][0]), "=r"(v[h][1]), "=r"(v[h][2]), "=r"(v[h][3]), "=r"(v[h][4]), "=r"(v[h][5]), "=r"(v[h][6]), "=r"(v[h][7]),
+                      "=r"(v[h][8]), "=r"(v[h][9]), "=r"(v[h][10]), "=r"(v[h][11]), "=r"(v[h][12]), "=r"(v[h][13]), "=r"(v[h][14]), "=r"(v[h][15]),
+                      "=r"(v[h][16]), "=r"(v[h][17]), "=r"(v[h][18]), "=r"(v[h][19]), "=r"(v[h][20]), "=r"(v[h][21]), "=r"(v[h][22]), "=r"(v[h][23]),
+                      "=r"(v[h][24]), "=r"(v[h][25]), "=r"(v[h][26]), "=r"(v[h][27]), "=r"(v[h][28]), "=r"(v[h][29]), "=r"(v[h][30]), "=r"(v[h][31])
+                    : "r"(tb + 32u * h));
+            }
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty_bar[gu & 1])) : "memory");
+#pragma unroll
+            for (int h = 0; h < NLD; ++h)
+#pragma unroll
+                for (int k = 0; k < WORK; ++k) {
+                    float r;
+                    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(acc), "f"(__uint_as_float(v[h][(2 * k) & 31])), "f"(__uint_as_float(v[h][(2 * k + 1) & 31])));
+                    acc = r;
+                }
+        }
+        if (acc == 12345.f) sink[tid] = acc;
+    }
+    const long long t1 = clock64();
+    if (tid == 0) cycles[blockIdx.x] = t1 - t0;
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u));
+}
+
+int main()
+{
+    std::vector<__nv_bfloat16> hA(M_ * K_), hB(N_ * K_);
+    std::vector<float> fA(M_ * K_), fB(N_ * K_);
+    srand(1);
+    for (int i = 0; i < M_ * K_; ++i) { float v = (rand() % 2001 - 1000) / 1000.0f; hA[i] = __float2bfloat16(v); fA[i] = __bfloat162float(hA[i]); }
+    for (int i = 0; i < N_ * K_; ++i) { float v = (rand() % 2001 - 1000) / 1000.0f; hB[i] = __float2bfloat16(v); fB[i] = __bfloat162float(hB[i]); }
+    __nv_bfloat16 *dA, *dB; float *dO;
+    cudaMalloc(&dA, hA.size() * 2); cudaMalloc(&dB, hB.size() * 2); cudaMalloc(&dO, sizeof(float) * M_ * N_);
+    cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice);
+    cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice);
+    std::vector<float> ref(M_ * N_), got(M_ * N_);
+    for (int i = 0; i < M_; ++i)
+        for (int j = 0; j < N_; ++j) {
+            double s = 0;
+            for (int k = 0; k < K_; ++k) s += (double)fA[i * K_ + k] * fB[j * K_ + k];
+            ref[i * N_ + j] = (float)s;
+        }
+    for (int variant = 0; variant < 1; ++variant) {
+        cudaMemset(dO, 0xff, sizeof(float) * M_ * N_);
+        probe<<<1, 128>>>(dA, dB, dO, variant);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("variant %d: CUDA error %s\n", variant, cudaGetErrorString(e)); return 1; }
+        cudaMemcpy(got.data(), dO, sizeof(float) * M_ * N_, cudaMemcpyDeviceToHost);
+        double maxerr = 0; int bad = 0;
+        for (int i = 0; i < M_ * N_; ++i) { double d = fabs((double)got[i] - ref[i]); if (!(d <= 1e-3)) ++bad; if (d > maxerr || d != d) maxerr = d; }
+        printf("variant %d (LBO/SBO %s): max |err| = %.3g, mismatches = %d of %d; got[0..3] = %g %g %g %g  ref = %g %g %g %g; got[row1] %g ref %g\n",
+               variant, variant == 0 ? "k-plane/row-group" : "swapped", maxerr, bad, M_ * N_, got[0], got[1], got[2], got[3], ref[0], ref[1], ref[2], ref[3],
+               got[N_], ref[N_]);
+    }
+    long long *dc; cudaMalloc(&dc, 8 * 296);
+    for (int blocks : {1, 148, 296}) {
+        for (int ncols : {128, 256}) {
+            const int reps = 2000;
+            if (ncols == 128) mma_rate<128><<<blocks, 128>>>(dA, dB, dc, reps); else mma_rate<256><<<blocks, 128>>>(dA, dB, dc, reps);
+            cudaError_t e = cudaDeviceSynchronize();
+            long long hc[296]; cudaMemcpy(hc, dc, 8 * blocks, cudaMemcpyDeviceToHost);
+            printf("MMA M=128 N=%d K=16 bf16, %d CTAs: %s  %.1f cycles per MMA (CTA 0), %.0f flop/clk/CTA\n", ncols, blocks, cudaGetErrorString(e),
+                   (double)hc[0] / reps, 2.0 * 128 * ncols * 16 / ((double)hc[0] / reps));
+        }
+    }
+    float *sink; cudaMalloc(&sink, 4 * 288);
+    {
+        const int units = 4000;
+        auto report = [&](const char *name) {
+            cudaError_t e = cudaDeviceSynchronize();
+            long long hc[296]; cudaMemcpy(hc, dc, 8 * 296, cudaMemcpyDeviceToHost);
+            printf("pipeline probe %-34s: %s  %.1f cycles per unit per CTA (2 CTAs/SM)\n", name, cudaGetErrorString(e), (double)hc[5] / units);
+        };
+        pipe_probe<0, 1><<<296, 288>>>(dA, dB, dc, sink, units); report("1 LDTM, no work");
+        pipe_probe<0, 2><<<296, 288>>>(dA, dB, dc, sink, units); report("2 LDTM, no work");
+        pipe_probe<16, 2><<<296, 288>>>(dA, dB, dc, sink, units); report("2 LDTM + 32 dependent min3");
+        pipe_probe<16, 2><<<148, 288>>>(dA, dB, dc, sink, units); report("same, 1 CTA/SM");
+    }
+    return 0;
+}

@@ -28,7 +28,9 @@ def child():
     i2 = torch.empty(B, M, dtype=torch.int32, device=dev)
     sp = torch.cuda.current_stream().cuda_stream
 
-    def step(k, flags=0):
+    TENSOR = 4 if os.environ.get("GEOM_BENCH_TENSOR") else 0
+
+    def step(k, flags=TENSOR):
         a, b = sets[k % len(sets)]
         rc = L.geom_chamfer_fwd(B, N, a.data_ptr(), M, b.data_ptr(), None, i1.data_ptr(), None, i2.data_ptr(),
                                 ws.data_ptr(), wsb, flags, sp)
