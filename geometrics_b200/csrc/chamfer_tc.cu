@@ -147,9 +147,9 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
 {
     unsigned done = 0;
     while (!done) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(done)
-                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)  // suspend-time hint (ns): park instead of spinning
                      : "memory");
     }
 }
@@ -170,7 +170,8 @@ __global__ void __launch_bounds__(kThreads, 2) search_kernel(const SearchArgs2 b
     const SearchArgs &a = both.dir[blockIdx.z];
     __shared__ __align__(128) uint4 sA[kRB][2][128];      // [row block][k-chunk][row]   canonical no-swizzle K-major
     __shared__ __align__(128) uint4 sB[2][2][kTileCols];  // [buffer][k-chunk][row]
-    __shared__ __align__(8) unsigned long long full_bar[2], empty_bar[2];
+    __shared__ __align__(16) float sX[4][kTileCols * 3];  // exact fp32 coordinates of the last four candidate tiles
+    __shared__ __align__(8) unsigned long long full_bar[2], empty_bar[2], x_bar[4];
     __shared__ unsigned tmem_slot;
     __shared__ float s_part[kRB][2][128];                 // per (row block, column half, row): partial minima
     __shared__ int s_pidx[kRB][128];
@@ -191,6 +192,7 @@ __global__ void __launch_bounds__(kThreads, 2) search_kernel(const SearchArgs2 b
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&full_bar[i])), "r"(1u));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&empty_bar[i])), "r"(8u));
         }
+        for (int i = 0; i < 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&x_bar[i])), "r"(32u));
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
     const uint4 *gB = a.formB + (size_t)bi * a.nc_pad * 2;
@@ -213,26 +215,36 @@ __global__ void __launch_bounds__(kThreads, 2) search_kernel(const SearchArgs2 b
         // ================================ producer ================================
         // D = f32, A = B = bf16, both K-major, N = 128, M = 128
         const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(kTileCols >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
-        auto load_tile = [&](int tile, int buf) {  // 128 rows x 2 chunks = 256 16-byte copies, 8 per lane
+        const float *cexact = a.cxyz + (size_t)bi * a.nc_full * 3;
+        auto load_tile = [&](int tile) {
+            // packed operands: 128 rows x 2 chunks = 256 16-byte copies, 8 per lane
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int c = lane + 32 * i;
-                cp_async16(&sB[buf][c & 1][c >> 1], &gB[(size_t)tile * kTileCols * 2 + c]);
+                cp_async16(&sB[tile & 1][c & 1][c >> 1], &gB[(size_t)tile * kTileCols * 2 + c]);
+            }
+            // exact coordinates: 384 floats, 12 per lane (4-byte copies: no alignment assumption on the caller's array)
+            const int last = a.nc_full * 3 - 1;
+#pragma unroll
+            for (int i = 0; i < 12; ++i) {
+                const int e = lane + 32 * i;
+                cp_async4(&sX[tile & 3][e], &cexact[min(tile * kTileCols * 3 + e, last)]);
             }
             cp_async_commit();
         };
-        load_tile(0, 0);
-        for (int ts = 0; ts < 2 * ntiles; ++ts) {  // tile sequence: pass 0 tiles, then pass 1 tiles
-            // this tile's candidates have landed (issued one tile ago); make them visible to the tensor core
+        load_tile(0);
+        for (int ts = 0; ts < ntiles; ++ts) {
+            // this tile has landed (issued one tile ago): visible to the tensor core and to the scanners
             cp_async_wait_all();
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(&x_bar[ts & 3]);
             __syncwarp();
             const int gu0 = ts * kRB;
-            if (ts + 1 < 2 * ntiles) {
-                // the other buffer was read by the MMAs of tile ts-1; the last of them is unit gu0-1
+            if (ts + 1 < ntiles) {
+                // the other operand buffer was read by the MMAs of tile ts-1; the last of them is unit gu0-1.
+                // (sX[(ts+1)&3] was last used by tile ts-3, long retired: scanners lag the MMAs by < 2 units.)
                 if (gu0 > 0) mbar_wait(&full_bar[(gu0 - 1) & 1], (unsigned)(((gu0 - 1) >> 1) & 1));
-                const int tn = (ts + 1 >= ntiles) ? ts + 1 - ntiles : ts + 1;
-                load_tile(tn, (ts + 1) & 1);
+                load_tile(ts + 1);
             }
 #pragma unroll
             for (int rb = 0; rb < kRB; ++rb) {
@@ -257,21 +269,21 @@ __global__ void __launch_bounds__(kThreads, 2) search_kernel(const SearchArgs2 b
         // ================================ scanners ================================
         const int half = warp >> 2;               // column half of the tile this thread scans
         const int rloc = (warp & 3) * 32 + lane;  // row inside a 128-row block == TMEM lane
-        float qx[kRB], qy[kRB], qz[kRB], acc[kRB], thr[kRB];  // acc: pass 0 = min of dt, pass 1 = best exact distance
+        float qx[kRB], qy[kRB], qz[kRB], mt[kRB], best[kRB];  // mt: running min of dt; best: exact distance so far
         int bidx[kRB];
 #pragma unroll
         for (int rb = 0; rb < kRB; ++rb) {
             const int qrow = min(row0 + rb * 128 + rloc, a.nq - 1);
             const float *q = a.qxyz + ((size_t)bi * a.nq + qrow) * 3;
             qx[rb] = q[0], qy[rb] = q[1], qz[rb] = q[2];
-            acc[rb] = __int_as_float(0x7f800000);
-            thr[rb] = acc[rb];
+            // padding rows (zero operand: every dt is 0) start at -inf so that nothing ever passes their filter
+            mt[rb] = (row0 + rb * 128 + rloc < a.nq) ? __int_as_float(0x7f800000) : __int_as_float(0xff800000);
+            best[rb] = __int_as_float(0x7f800000);
             bidx[rb] = 0;
         }
         const float rmax = __uint_as_float(*both.rmax_bits);
         // |dt - d| <= eps; inputs too large for the bf16 split to stay finite disable the filter (eps = inf)
-        const float eps = (rmax < 1.0e15f) ? both.eps_scale * rmax * rmax : __int_as_float(0x7f800000);
-        const float *cand = a.cxyz + (size_t)bi * a.nc_full * 3;
+        const float eps2 = (rmax < 1.0e15f) ? 2.0f * both.eps_scale * rmax * rmax : __int_as_float(0x7f800000);
         // block minimum of 32 approximate distances with 3-input minima (0.5 instruction per pair)
         auto block_min = [&](const unsigned(&v)[32]) {
             float bm = min3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
@@ -279,62 +291,50 @@ __global__ void __launch_bounds__(kThreads, 2) search_kernel(const SearchArgs2 b
             for (int k = 3; k + 1 < 32; k += 2) bm = min3(bm, __uint_as_float(v[k]), __uint_as_float(v[k + 1]));
             return fminf(bm, __uint_as_float(v[31]));
         };
-        // Two passes over the candidate tiles:
-        //   pass 0: mt = min_j dt(i,j), nothing else (3-input minima only, no branches);
-        //   pass 1: every j with dt(i,j) <= mt + 2 eps is re-evaluated exactly, in ascending order.
-        // The true nearest neighbour j* is in that set: dt(j*) <= d(j*) + eps <= d(jt) + eps <= dt(jt) + 2 eps
-        // = mt + 2 eps (jt = argmin dt).  A fixed threshold keeps the exact re-evaluations to ~1 per query.
-        for (int pass = 0; pass < 2; ++pass) {
-            if (pass) {
+        // One sweep.  mt = running minimum of dt over the candidates seen so far (this block included); a
+        // candidate is re-evaluated exactly when dt <= mt + 2 eps.  The final survivors of a fixed-threshold
+        // filter {dt <= mt_final + 2 eps} are a subset (mt only decreases), and the true nearest neighbour
+        // j* is among them: dt(j*) <= d(j*) + eps <= d(jt) + eps <= dt(jt) + 2 eps = mt_final + 2 eps with
+        // jt = argmin dt.  Exact coordinates of the tile come from shared memory (staged by the producer).
+        for (int t = 0; t < ntiles; ++t) {
+            mbar_wait(&x_bar[t & 3], (unsigned)((t >> 2) & 1));
+            const float *xs = &sX[t & 3][half * 64 * 3];
+            const int c0 = t * kTileCols + half * 64;
 #pragma unroll
-                for (int rb = 0; rb < kRB; ++rb) s_part[rb][half][rloc] = acc[rb];
-                asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight scanner warps only
+            for (int rb = 0; rb < kRB; ++rb) {
+                const int gu = t * kRB + rb;
+                mbar_wait(&full_bar[gu & 1], (unsigned)((gu >> 1) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const unsigned tbase = tmem + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)((gu & 1) * kTileCols + half * 64);
+                unsigned va[32], vb[32];
+                GEOM_TMEM_LD32(va, tbase);
+                GEOM_TMEM_LD32(vb, tbase + 32u);
+                GEOM_TMEM_WAIT(va);
+                GEOM_TMEM_WAIT(vb);
+                // the values are in registers: hand the accumulator back to the tensor core
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[gu & 1]);
 #pragma unroll
-                for (int rb = 0; rb < kRB; ++rb) {
-                    thr[rb] = fminf(s_part[rb][0][rloc], s_part[rb][1][rloc]) + 2.0f * eps;
-                    // padding rows (zero operand: every dt is 0) must not turn every candidate into a survivor
-                    if (row0 + rb * 128 + rloc >= a.nq) thr[rb] = __int_as_float(0xff800000);
-                    acc[rb] = __int_as_float(0x7f800000);
-                }
-            }
-            for (int t = 0; t < ntiles; ++t) {
-                const int c0 = t * kTileCols + half * 64;
+                for (int hb = 0; hb < 2; ++hb) {
+                    const unsigned(&v)[32] = hb ? vb : va;
+                    const float bm = block_min(v);
+                    mt[rb] = fminf(mt[rb], bm);
+                    const float thr = mt[rb] + eps2;
+                    if (!(bm > thr)) {  // a candidate inside the window (NaN counts as inside)
+                        unsigned mask = 0;
 #pragma unroll
-                for (int rb = 0; rb < kRB; ++rb) {
-                    const int gu = pass * nunits + t * kRB + rb;
-                    mbar_wait(&full_bar[gu & 1], (unsigned)((gu >> 1) & 1));
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const unsigned tbase = tmem + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)((gu & 1) * kTileCols + half * 64);
-                    unsigned va[32], vb[32];
-                    GEOM_TMEM_LD32(va, tbase);
-                    GEOM_TMEM_LD32(vb, tbase + 32u);
-                    GEOM_TMEM_WAIT(va);
-                    GEOM_TMEM_WAIT(vb);
-                    // the values are in registers: hand the accumulator back to the tensor core
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&empty_bar[gu & 1]);
-                    if (!pass) {
-                        acc[rb] = fminf(acc[rb], fminf(block_min(va), block_min(vb)));
-                    } else {
-#pragma unroll
-                        for (int hb = 0; hb < 2; ++hb) {
-                            const unsigned(&v)[32] = hb ? vb : va;
-                            if (!(block_min(v) > thr[rb])) {  // a candidate inside the window (NaN counts as inside)
-                                unsigned mask = 0;
-#pragma unroll
-                                for (int k = 0; k < 32; ++k) mask |= (!(__uint_as_float(v[k]) > thr[rb])) ? (1u << k) : 0u;
-                                while (mask) {  // ascending index order
-                                    const int k = __ffs(mask) - 1;
-                                    mask &= mask - 1;
-                                    const int j = c0 + hb * 32 + k;
-                                    if (j < a.nc) {
-                                        const float d = sqdist_ref(qx[rb], qy[rb], qz[rb], cand[j * 3 + 0], cand[j * 3 + 1], cand[j * 3 + 2]);
-                                        if (d < acc[rb]) {  // ascending j + strict '<': lowest index among exact ties
-                                            acc[rb] = d;
-                                            bidx[rb] = j;
-                                        }
-                                    }
+                        for (int k = 0; k < 32; ++k) mask |= (!(__uint_as_float(v[k]) > thr)) ? (1u << k) : 0u;
+                        while (mask) {  // ascending index order
+                            const int k = hb * 32 + __ffs(mask) - 1;
+                            mask &= mask - 1;
+                            const int j = c0 + k;
+                            if (j < a.nc) {
+                                const float *cx = xs + k * 3;
+                                const float d = sqdist_ref(qx[rb], qy[rb], qz[rb], cx[0], cx[1], cx[2]);
+                                if (d < best[rb]) {  // ascending j + strict '<': lowest index among exact ties
+                                    best[rb] = d;
+                                    bidx[rb] = j;
                                 }
                             }
                         }
@@ -342,6 +342,7 @@ __global__ void __launch_bounds__(kThreads, 2) search_kernel(const SearchArgs2 b
                 }
             }
         }
+        float (&acc)[kRB] = best;
         // merge the two column halves of every row: smaller exact distance, lower index on ties
         if (half == 1) {
 #pragma unroll
