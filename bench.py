@@ -305,6 +305,12 @@ def run_product(args):
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        traffic, traffic_src = None, None
+        try:  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[dom_name]
+            traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+        except Exception:
+            pass
         alg_bytes = 16 * B * (N_PTS + M_PTS)  # read 12 B/point, write one int32 index/point
         dom_ms = kern_ms_max
         ach = alg_bytes / (dom_ms * 1e-3) / 1e9
@@ -323,7 +329,7 @@ def run_product(args):
             "kernels": {k_: {"ms_per_launch": v[0] / v[1], "launches": v[1], "share_of_step": v[0] / args.steps / ms_step}
                         for k_, v in kern.items()},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                         "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
                          "kernel": dom_name, "kernel_ms": dom_ms, "algorithmic_bytes": alg_bytes,
                          "note": "brute-force NN is FP32-issue bound, not HBM bound (SURVEY.md 8d); see fp32 below",
                          "fp32": {"lane_ops_per_launch": lane_ops, "achieved_tlops": lane_ops / (dom_ms * 1e-3) / 1e12,
