@@ -29,6 +29,7 @@ SYMBOLS = {
     "geom_prof_end": (_i, [C.POINTER(C.c_float), C.POINTER(_i)]),
     "geom_prof_kernel_name": (C.c_char_p, [_i]),
     "geom_chamfer_workspace_bytes": (_sz, [_i, _i, _i]),
+    "geom_chamfer_tensor_workspace_bytes": (_sz, [_i, _i, _i]),
     "geom_chamfer_fwd": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _u, _vp]),
     "geom_host_ctx_create": (_i, [C.POINTER(_vp)]),
     "geom_host_ctx_destroy": (_i, [_vp]),

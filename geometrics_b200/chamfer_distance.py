@@ -34,7 +34,7 @@ def chamfer_forward(xyz1: torch.Tensor, xyz2: torch.Tensor, *, exact_tail: bool 
         idx2 = torch.empty((b, m), dtype=torch.int32, device=dev)
         dist1 = torch.empty((b, n), dtype=torch.float32, device=dev) if want_dist else None
         dist2 = torch.empty((b, m), dtype=torch.float32, device=dev) if want_dist else None
-        ws_bytes = L.geom_chamfer_workspace_bytes(b, n, m)
+        ws_bytes = (L.geom_chamfer_tensor_workspace_bytes if tensor else L.geom_chamfer_workspace_bytes)(b, n, m)
         ws = torch.empty((max(ws_bytes, 16) + 15) // 16 * 2, dtype=torch.int64, device=dev)
         flags = (_lib.GEOM_FLAG_EXACT_TAIL if exact_tail else 0) | (_lib.GEOM_FLAG_ONEWAY if oneway else 0) \
             | (_lib.GEOM_FLAG_TENSOR if tensor else 0)

@@ -503,8 +503,14 @@ using namespace geom;
 extern "C" size_t geom_chamfer_workspace_bytes(int b, int n, int m)
 {
     if (b < 0 || n < 0 || m < 0) return 0;
-    const size_t keys = sizeof(u64) * (size_t)b * ((size_t)n + (size_t)m) + 16;  // keys + the work ticket
-    const size_t tc = chamfer_tc::workspace_bytes(b, n, m);                      // packed bf16 operands
+    return sizeof(u64) * (size_t)b * ((size_t)n + (size_t)m) + 16;  // keys + the work ticket
+}
+
+extern "C" size_t geom_chamfer_tensor_workspace_bytes(int b, int n, int m)
+{
+    if (b < 0 || n < 0 || m < 0) return 0;
+    const size_t keys = geom_chamfer_workspace_bytes(b, n, m);  // degenerate sizes fall back to the plain kernels
+    const size_t tc = chamfer_tc::workspace_bytes(b, n, m);     // packed bf16 operands
     return keys > tc ? keys : tc;
 }
 
@@ -531,7 +537,7 @@ extern "C" int geom_chamfer_fwd(int b, int n, const float *xyz1, int m, const fl
 
     cudaError_t e = cudaSuccess;
     if ((flags & GEOM_FLAG_TENSOR) && !(flags & GEOM_FLAG_ONEWAY) && n_scan > 0 && m_scan > 0 && b <= 65535) {
-        const size_t need = geom_chamfer_workspace_bytes(b, n, m);
+        const size_t need = geom_chamfer_tensor_workspace_bytes(b, n, m);
         if (!workspace || workspace_bytes < need || ((uintptr_t)workspace & 15u)) return GEOM_ERR_WORKSPACE;
         return status_from_cuda(chamfer_tc::launch(b, n, xyz1, m, xyz2, n_scan, m_scan, zero1, zero2, dist1, idx1, dist2,
                                                    idx2, workspace, st));

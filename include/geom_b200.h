@@ -82,6 +82,8 @@ GEOM_API const char *geom_prof_kernel_name(int id);
  * Inputs must be finite.
  * ------------------------------------------------------------------------------------------- */
 GEOM_API size_t geom_chamfer_workspace_bytes(int b, int n, int m);
+/* workspace needed when GEOM_FLAG_TENSOR is set (packed bf16 operands: 64 B per padded point); 16-byte aligned */
+GEOM_API size_t geom_chamfer_tensor_workspace_bytes(int b, int n, int m);
 GEOM_API int geom_chamfer_fwd(int b, int n, const float *xyz1, int m, const float *xyz2,
                      float *dist1, int *idx1, float *dist2, int *idx2,
                      void *workspace, size_t workspace_bytes, unsigned flags, geom_stream_t stream);

@@ -22,7 +22,7 @@ def child():
     B, N, M = 32, 10000, 10000
     sets = [(synth.random_points(B, N, 41 + i).to(dev), synth.random_points(B, M, 141 + i).to(dev)) for i in range(8)]
     L = g.lib()
-    wsb = L.geom_chamfer_workspace_bytes(B, N, M)
+    wsb = max(L.geom_chamfer_workspace_bytes(B, N, M), L.geom_chamfer_tensor_workspace_bytes(B, N, M))
     ws = torch.empty(wsb // 8 + 1, dtype=torch.int64, device=dev)
     i1 = torch.empty(B, N, dtype=torch.int32, device=dev)
     i2 = torch.empty(B, M, dtype=torch.int32, device=dev)
