@@ -49,6 +49,7 @@ SYMBOLS = {
     "geom_csr_fill": (_i, [_i, _vp, _i, _vp, _vp, _vp, _vp]),
     "geom_csr_spmm": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "geom_zeron_gcn_workspace_bytes": (_sz, [_i, _i, _i]),
+    "geom_zeron_gcn_tensor_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "geom_zeron_gcn_fwd": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
     "geom_zeron_gcn_bwd_smooth": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
 }

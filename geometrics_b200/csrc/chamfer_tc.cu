@@ -181,7 +181,6 @@ __global__ void __launch_bounds__(kThreads, 2) search_kernel(const SearchArgs2 b
     const int row0 = blockIdx.x * kRowsPerCta;
     if (row0 >= a.nq_pad) return;  // the grid covers the longer of the two directions
     const int ntiles = (a.nc + kTileCols - 1) / kTileCols;
-    const int nunits = ntiles * kRB;
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"((unsigned)kTmemCols));

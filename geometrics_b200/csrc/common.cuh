@@ -134,6 +134,14 @@ cudaError_t launch(int b, int n, const float *xyz1, int m, const float *xyz2, in
                    int zero2, float *dist1, int *idx1, float *dist2, int *idx2, void *workspace, cudaStream_t st);
 }  // namespace chamfer_tc
 
+// tensor-core (3xTF32 tcgen05) feature GEMM of the 0N-GCN layer (gcn_tc.cu)
+namespace gcn_tc {
+bool supported(int N);
+size_t workspace_bytes(int K, int N);
+cudaError_t launch(int M, int K, int N, const float *X, const float *W, const float *bias, float *Y, float *T,
+                   int ksplit, int ldt, int relu, void *wsplit, cudaStream_t st);
+}  // namespace gcn_tc
+
 inline int status_from_cuda(cudaError_t e) { return e == cudaSuccess ? GEOM_OK : (int)e; }
 
 }  // namespace geom

@@ -382,12 +382,20 @@ extern "C" size_t geom_zeron_gcn_workspace_bytes(int b, int V, int ksplit)
     return sizeof(float) * (size_t)b * V * ldt;
 }
 
+extern "C" size_t geom_zeron_gcn_tensor_workspace_bytes(int b, int V, int in_features, int out_features, int ksplit)
+{
+    if (b < 0 || V < 0 || in_features < 0 || out_features < 0 || ksplit < 0) return 0;
+    const size_t t = (geom_zeron_gcn_workspace_bytes(b, V, ksplit) + 255) & ~(size_t)255;
+    return t + gcn_tc::workspace_bytes(in_features, out_features);
+}
+
 extern "C" int geom_zeron_gcn_fwd(int b, int V, int in_features, int out_features, int ksplit,
                                   const float *X, const float *W, const float *bias,
                                   const int *row_ptr, const int *col_idx, const float *val, float *Y,
-                                  int relu, void *workspace, size_t workspace_bytes, geom_stream_t stream)
+                                  int flags, void *workspace, size_t workspace_bytes, geom_stream_t stream)
 {
     using namespace geom::gcn;
+    const int relu = flags & 1;
     if (b < 0 || V < 0 || in_features < 0 || out_features < 0 || ksplit < 0 || ksplit > out_features)
         return GEOM_ERR_INVALID_ARG;
     const long long M = (long long)b * V;
@@ -411,7 +419,15 @@ extern "C" int geom_zeron_gcn_fwd(int b, int V, int in_features, int out_feature
     g.ksplit = ksplit;
     g.ldt = (ksplit + 3) & ~3;
     g.relu = relu;
-    {
+    const bool tensor = (flags & 2) && gcn_tc::supported(out_features) && in_features >= 8;
+    if (tensor) {
+        const size_t tneed = geom_zeron_gcn_tensor_workspace_bytes(b, V, in_features, out_features, ksplit);
+        if (!workspace || workspace_bytes < tneed || ((uintptr_t)workspace & 15u)) return GEOM_ERR_WORKSPACE;
+        void *wsplit = (char *)workspace + ((need + 255) & ~(size_t)255);
+        prof::Scope ps(st, prof::kGcnGemm);
+        cudaError_t e = gcn_tc::launch((int)M, in_features, out_features, X, W, bias, Y, g.T, ksplit, g.ldt, relu, wsplit, st);
+        if (e != cudaSuccess) return status_from_cuda(e);
+    } else {
         prof::Scope ps(st, prof::kGcnGemm);
         if (out_features <= kSkinnyMaxN) {
             skinny_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(g);

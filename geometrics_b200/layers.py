@@ -114,7 +114,7 @@ class ZeroNGCNFunction(torch.autograd.Function):
     """Y = [adj . (XW)[:, :k] | (XW)[:, k:]] + bias for X (B,V,in), W (in,out), k = ksplit."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, csr, ksplit, relu):
+    def forward(ctx, x, weight, bias, csr, ksplit, relu, tensor=False):
         L = _lib.lib()
         xc, wc = x.detach().contiguous(), weight.detach().contiguous()
         bc = bias.detach().contiguous() if bias is not None else None
@@ -123,11 +123,12 @@ class ZeroNGCNFunction(torch.autograd.Function):
         dev = xc.device
         with torch.cuda.device(dev):
             y = torch.empty((b, v, fout), dtype=torch.float32, device=dev)
-            wsb = L.geom_zeron_gcn_workspace_bytes(b, v, ksplit)
+            wsb = (L.geom_zeron_gcn_tensor_workspace_bytes(b, v, fin, fout, ksplit) if tensor
+                   else L.geom_zeron_gcn_workspace_bytes(b, v, ksplit))
             ws = torch.empty(max(wsb // 4, 4), dtype=torch.float32, device=dev)
             _lib.check(L.geom_zeron_gcn_fwd(b, v, fin, fout, ksplit, xc.data_ptr(), wc.data_ptr(),
                                             bc.data_ptr() if bc is not None else None, csr.row_ptr.data_ptr(),
-                                            csr.col_idx.data_ptr(), csr.val.data_ptr(), y.data_ptr(), int(relu),
+                                            csr.col_idx.data_ptr(), csr.val.data_ptr(), y.data_ptr(), int(relu) | (2 if tensor else 0),
                                             ws.data_ptr(), ws.numel() * 4, _lib.current_stream_ptr(dev)),
                        "geom_zeron_gcn_fwd")
         ctx.save_for_backward(xc, wc, y if relu else None)
@@ -156,10 +157,13 @@ class ZeroNGCNFunction(torch.autograd.Function):
             dw = torch.matmul(xc.reshape(-1, xc.shape[-1]).t(), ds.reshape(-1, fout))
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy.sum(dim=(0, 1))
-        return dx, dw, db, None, None, None
+        return dx, dw, db, None, None, None, None
 
 
-def zeron_gcn(x, weight, bias, adj, split: int, activation=None):
+TENSOR_GEMM = False  # feature GEMM on the tensor cores (3xTF32 tcgen05) when the shape allows
+
+
+def zeron_gcn(x, weight, bias, adj, split: int, activation=None, tensor=None):
     """Functional form.  ``x`` (B,V,in) or (V,in); ``adj`` dense (V,V) or a CsrAdjacency; the first
     ``out // split`` output columns are neighbour-averaged (split = 3: image GCN, 10: encoder GCN)."""
     _lib.require_cuda_f32("input", x)
@@ -181,7 +185,8 @@ def zeron_gcn(x, weight, bias, adj, split: int, activation=None):
     if weight.shape[0] != x.shape[2]:
         raise ValueError(f"weight is {tuple(weight.shape)} but input has {x.shape[2]} features")
     fuse_relu = activation is F.relu or activation is torch.relu
-    y = ZeroNGCNFunction.apply(x, weight, bias, csr, weight.shape[1] // split, fuse_relu)
+    y = ZeroNGCNFunction.apply(x, weight, bias, csr, weight.shape[1] // split, fuse_relu,
+                               TENSOR_GEMM if tensor is None else bool(tensor))
     if squeeze:
         y = y.squeeze(0)
     if activation is None or fuse_relu:

@@ -192,8 +192,11 @@ GEOM_API int geom_sample_bwd(int b, int V, int F, const int64_t *faces, int num,
  *   geom_csr_count(V, adj, transpose, row_cnt, row_ptr): row_ptr[0..V] (exclusive scan of the per-row
  *     non-zero counts; row_cnt is a V-int scratch).  The caller reads row_ptr[V] = nnz, allocates
  *     col_idx / val, and calls geom_csr_fill.  transpose != 0 builds the CSR of adj^T (backward).
- * geom_zeron_gcn_fwd: X (B,V,in), W (in,out), bias (out) or NULL, Y (B,V,out); relu != 0 fuses
- *   max(.,0); workspace >= geom_zeron_gcn_workspace_bytes(B,V,ksplit), 16-byte aligned.
+ * geom_zeron_gcn_fwd: X (B,V,in), W (in,out), bias (out) or NULL, Y (B,V,out); flags bit 0 fuses
+ *   max(.,0); flags bit 1 (GEOM_GCN_TENSOR) runs the feature GEMM on the tensor cores (tcgen05, three TF32
+ *   MMAs per product term = fp32-level accuracy; 16 <= out <= 256, else the CUDA-core GEMM is used);
+ *   workspace >= geom_zeron_gcn_workspace_bytes(B,V,ksplit) -- or geom_zeron_gcn_tensor_workspace_bytes
+ *   (B,V,in,out,ksplit) with GEOM_GCN_TENSOR -- 16-byte aligned.
  * geom_zeron_gcn_bwd_smooth: dS (B,V,out) = [ adj^T . dY[:, :ksplit] | dY[:, ksplit:] ] from the CSR
  *   of adj^T; the caller finishes with the two plain GEMMs dX = dS W^T, dW = X^T dS.
  * fp32 throughout (fp32 accumulate); differs from the dense reference only by summation order.
@@ -206,10 +209,13 @@ GEOM_API int geom_csr_fill(int V, const float *adj, int transpose, const int *ro
  * `torch.matmul(adj_orig, positions)` of the Laplacian regulariser (utils.py:654-662). */
 GEOM_API int geom_csr_spmm(int b, int V, int C, const int *row_ptr, const int *col_idx, const float *val,
                   const float *X, float *Y, geom_stream_t stream);
+#define GEOM_GCN_RELU 1
+#define GEOM_GCN_TENSOR 2
 GEOM_API size_t geom_zeron_gcn_workspace_bytes(int b, int V, int ksplit);
+GEOM_API size_t geom_zeron_gcn_tensor_workspace_bytes(int b, int V, int in_features, int out_features, int ksplit);
 GEOM_API int geom_zeron_gcn_fwd(int b, int V, int in_features, int out_features, int ksplit, const float *X,
                        const float *W, const float *bias, const int *row_ptr, const int *col_idx,
-                       const float *val, float *Y, int relu, void *workspace, size_t workspace_bytes,
+                       const float *val, float *Y, int flags, void *workspace, size_t workspace_bytes,
                        geom_stream_t stream);
 GEOM_API int geom_zeron_gcn_bwd_smooth(int b, int V, int out_features, int ksplit, const int *t_row_ptr,
                               const int *t_col_idx, const float *t_val, const float *dY, float *dS,

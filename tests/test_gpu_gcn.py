@@ -195,3 +195,36 @@ def test_regularisers_vs_torch(cuda):
         close(p1.grad, p2.grad.cpu().numpy(), 1e-5, "d lap")
     e = U.batch_calc_edge(pos, info)
     assert e.shape == () and float(e) > 0
+
+
+@pytest.mark.parametrize("shape", [(3, 482, 963, 192, 3), (2, 642, 256, 256, 3), (2, 482, 192, 192, 3), (2, 482, 210, 250, 10),
+                                   (2, 100, 37, 50, 10), (1, 482, 1155, 192, 3), (4, 2562, 256, 256, 3), (1, 130, 8, 16, 3)])
+def test_tensor_gemm_layer_vs_torch(cuda, shape):
+    """GEOM_GCN_TENSOR (tcgen05, 3xTF32) forward against the fp32 dense-adjacency torch expression: the same
+    1e-5 budget as the CUDA-core GEMM."""
+    import geometrics_b200 as g
+    from geometrics_b200 import synth
+
+    b, v, fin, fout, split = shape
+    gen = torch.Generator().manual_seed(7)
+    if v in (482, 642, 2562):
+        faces = {482: synth.uv_sphere(32, 15), 642: synth.icosphere(3), 2562: synth.icosphere(4)}[v][1]
+        adj = g.adj_init(faces)["adj"].to(cuda)
+    else:
+        a = (torch.rand(v, v, generator=gen) < 0.05).float()
+        adj = g.normalize_adj(((a + a.t() + torch.eye(v)) > 0).float()).to(cuda)
+    x = torch.randn(b, v, fin, generator=gen).to(cuda)
+    w = (torch.randn(fin, fout, generator=gen) / fin ** 0.5).to(cuda)
+    bias = torch.randn(fout, generator=gen).to(cuda)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        want = R.zeron_gcn(x.double(), w.double(), bias.double(), adj.double(), split).float()
+        for act in (None, F.relu):
+            got = g.zeron_gcn(x, w, bias, adj, split, act, tensor=True)
+            ref = want if act is None else act(want)
+            close(got, ref.cpu().numpy(), 1e-5, f"tensor fwd {shape} {act}")
+        simt = g.zeron_gcn(x, w, bias, adj, split, None, tensor=False)
+        close(simt, want.cpu().numpy(), 1e-5, f"cuda-core fwd {shape}")
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev

@@ -170,6 +170,10 @@ def main():
     flops = 2 * 32 * 2562 * 256 * 256 + 2 * 32 * csr.nnz * 85
     emit("C4 0N-GCN layer fwd B=32 V=2562 256->256 (k=85)", ms, rms, alg, flops, "flop", prof(f),
          note="reference arm = torch dense-adjacency expression (cuBLAS fp32, TF32 off)")
+    f = lambda i: g.zeron_gcn(xs[i % 4], w, bias, csr, 3, tensor=True)
+    ms = timeit(f, reps=20)
+    emit("C4 0N-GCN layer fwd, tensor-core GEMM (tcgen05 3xTF32)", ms, rms, alg, flops, "flop", prof(f),
+         note="same layer with GEOM_GCN_TENSOR")
     # the reference block's real layer shapes at V=482, B=16
     adj2 = g.adj_init(synth.uv_sphere(32, 15)[1])["adj"].to(dev)
     for fin, fout in ((963, 192), (192, 192), (192, 3)):
@@ -180,6 +184,9 @@ def main():
         ms = timeit(f, reps=50)
         rms = timeit(lambda i: R.zeron_gcn(x, ww, bb, adj2, 3), reps=50)
         emit(f"0N-GCN layer fwd B=16 V=482 {fin}->{fout}", ms, rms, None, 2 * 16 * 482 * fin * fout, "flop", prof(f))
+        if fout >= 16:
+            f = lambda i: g.zeron_gcn(x, ww, bb, adj2, 3, tensor=True)
+            emit(f"0N-GCN layer fwd B=16 V=482 {fin}->{fout}, tensor-core GEMM", timeit(f, reps=50), rms, None, 2 * 16 * 482 * fin * fout, "flop", prof(f))
     # whole deformation block fwd+bwd (B=16, V=482, 963 features)
     block = g.BatchMeshDeformationBlock(963, 482).to(dev)
     pos = synth.mesh_batch(synth.uv_sphere(32, 15)[0], 16).to(dev)
