@@ -139,6 +139,15 @@ struct SearchArgs2 {
                    "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]),          \
                    "+r"(v[29]), "+r"(v[30]), "+r"(v[31])::"memory")
 
+// 64 consecutive columns of this warp's 32 TMEM lanes, load and wait in ONE statement (no register ties needed)
+__device__ __forceinline__ void tmem_ld64_wait(unsigned (&v)[64], unsigned taddr)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];\n\ttcgen05.wait::ld.sync.aligned;"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]), "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]), "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+                 : "r"(taddr)
+                 : "memory");
+}
+
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
@@ -379,6 +388,239 @@ __global__ void __launch_bounds__(kThreads, 2) search_kernel(const SearchArgs2 b
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((unsigned)kTmemCols));
 }
 
+
+// ------------------------------------------------------------------------------------------------------
+// scan_kernel: the same filter with the survivor work DEFERRED, one accumulator per warp group.
+//
+// A CTA owns 4 x 128 query rows (A operands resident in shared memory) and streams 128-candidate tiles.
+// Row block g has its own TMEM accumulator (128 columns) and its own group of four scanner warps (one per
+// TMEM lane quarter), so a thread owns one query row for the whole sweep:
+//   warp 16 (producer): cp.async candidate tiles into a 4-stage ring; per tile and group: wait empty[g] ->
+//                       tcgen05.mma M128 N128 K16 -> tcgen05.commit -> full[g]
+//   warps 0-15 (scanners, g = warp>>2): wait full[g] -> tcgen05.ld 2 x 64 columns -> arrive empty[g] ->
+//                       minima of the four 32-candidate blocks with 3-input min trees (0.5 instr / pair).
+// No exact arithmetic inside the sweep.  With mt = running minimum of dt for the row, a block whose
+// minimum bm satisfies bm <= mt + 2 eps is appended to the thread's EVENT list (predicated store, no
+// branch).  After the sweep (or when the list is nearly full) the thread re-evaluates with the exact
+// fp32 sequence every candidate of the listed blocks that still satisfy bm <= mt + 2 eps, in ascending
+// index order with strict '<'.  Correctness: the true nearest neighbour j* has dt(j*) <= d(j*) + eps <=
+// d(jt) + eps <= dt(jt) + 2 eps = mt_final + 2 eps (jt = argmin dt), mt only decreases, so the block of j*
+// is listed when it is scanned and survives every later re-check; candidates with the same exact distance
+// as j* satisfy the same bound, so the lowest index among ties is found too.
+// ------------------------------------------------------------------------------------------------------
+constexpr int kGroups = 4;
+constexpr int kScanThreads = kGroups * 128;
+constexpr int kScanKernelThreads = kScanThreads + 32;
+constexpr int kStages = 4;   // candidate-tile ring
+constexpr int kEvCap = 24;   // events per thread held in shared memory
+constexpr int kScanTmemCols = kGroups * kTileCols;
+struct ScanSmem {
+    uint4 sA[kGroups][2][128];           // [row block][k-chunk][row]  canonical no-swizzle K-major
+    uint4 sB[kStages][2][kTileCols];     // [stage][k-chunk][row]
+    uint2 ev[kEvCap][kScanThreads];      // (block index, block minimum of dt)
+    unsigned long long full_bar[kGroups], empty_bar[kGroups];
+    unsigned tmem_slot;
+};
+
+// minimum of 32 approximate distances: 16 three-input minima as a depth-4 tree
+__device__ __forceinline__ float tree_min32(const unsigned (&v)[32])
+{
+    float l1[12];
+#pragma unroll
+    for (int i = 0; i < 10; ++i)
+        l1[i] = min3(__uint_as_float(v[3 * i]), __uint_as_float(v[3 * i + 1]), __uint_as_float(v[3 * i + 2]));
+    l1[10] = __uint_as_float(v[30]);
+    l1[11] = __uint_as_float(v[31]);
+    const float a0 = min3(l1[0], l1[1], l1[2]), a1 = min3(l1[3], l1[4], l1[5]);
+    const float a2 = min3(l1[6], l1[7], l1[8]), a3 = min3(l1[9], l1[10], l1[11]);
+    return fminf(min3(a0, a1, a2), a3);
+}
+__device__ __forceinline__ float tree_min32o(const unsigned (&v)[64], int o)
+{
+    float l1[12];
+#pragma unroll
+    for (int i = 0; i < 10; ++i)
+        l1[i] = min3(__uint_as_float(v[o + 3 * i]), __uint_as_float(v[o + 3 * i + 1]), __uint_as_float(v[o + 3 * i + 2]));
+    l1[10] = __uint_as_float(v[o + 30]);
+    l1[11] = __uint_as_float(v[o + 31]);
+    const float a0 = min3(l1[0], l1[1], l1[2]), a1 = min3(l1[3], l1[4], l1[5]);
+    const float a2 = min3(l1[6], l1[7], l1[8]), a3 = min3(l1[9], l1[10], l1[11]);
+    return fminf(min3(a0, a1, a2), a3);
+}
+
+__global__ void __launch_bounds__(kScanKernelThreads, 1) scan_kernel(const SearchArgs2 both)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    ScanSmem &S = *reinterpret_cast<ScanSmem *>(smem_raw);
+    const SearchArgs &a = both.dir[blockIdx.z];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int bi = blockIdx.y;
+    const int row0 = blockIdx.x * kRowsPerCta;
+    if (row0 >= a.nq_pad) return;  // the grid covers the longer of the two directions
+    const int ntiles = (a.nc + kTileCols - 1) / kTileCols;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_slot)), "r"((unsigned)kScanTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 0) {
+        for (int i = 0; i < kGroups; ++i) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&S.full_bar[i])), "r"(1u));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&S.empty_bar[i])), "r"(4u));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    const uint4 *gB = a.formB + (size_t)bi * a.nc_pad * 2;
+    {
+        const uint4 *ga = a.formA + ((size_t)bi * a.nq_pad + row0) * 2;
+        for (int i = tid; i < kRowsPerCta * 2; i += kScanKernelThreads) {
+            const int r = i >> 1;
+            cp_async16(&S.sA[r >> 7][i & 1][r & 127], &ga[i]);
+        }
+        cp_async_commit();
+        cp_async_wait_all();
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem = S.tmem_slot;
+
+    if (warp == kGroups * 4) {
+        // ================================ producer ================================
+        const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(kTileCols >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
+        auto load_tile = [&](int tile) {
+            if (tile < ntiles) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {  // 128 rows x 2 chunks = 256 16-byte copies, 8 per lane
+                    const int c = lane + 32 * i;
+                    cp_async16(&S.sB[tile % kStages][c & 1][c >> 1], &gB[(size_t)tile * kTileCols * 2 + c]);
+                }
+            }
+            cp_async_commit();  // always: keeps the group count uniform
+        };
+        load_tile(0);
+        load_tile(1);
+        for (int t = 0; t < ntiles; ++t) {
+            // stage (t+2)%4 was last read by the MMAs of tile t-2; those completed before the scanners could
+            // release the accumulators that the MMAs of tile t-1 (already issued) waited for.
+            load_tile(t + 2);
+            asm volatile("cp.async.wait_group 2;" ::: "memory");  // tile t has landed
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+#pragma unroll
+            for (int g = 0; g < kGroups; ++g) {
+                if (t >= 1) mbar_wait(&S.empty_bar[g], (unsigned)((t - 1) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0) {
+                    const u64 da = make_desc(smem_u32(&S.sA[g][0][0]), 128 * 16, 128);
+                    const u64 db = make_desc(smem_u32(&S.sB[t % kStages][0][0]), kTileCols * 16, 128);
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem + (unsigned)(g * kTileCols)),
+                        "l"(da), "l"(db), "r"(idesc), "r"(0u)
+                        : "memory");
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&S.full_bar[g])) : "memory");
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ================================ scanners ================================
+        const int g = warp >> 2;         // row block == accumulator == warp group
+        const int rloc = (warp & 3) * 32 + lane;  // row inside the block == TMEM lane
+        const int qrow = row0 + g * 128 + rloc;
+        const bool valid = qrow < a.nq;
+        float qx, qy, qz;
+        {
+            const float *q = a.qxyz + ((size_t)bi * a.nq + min(qrow, a.nq - 1)) * 3;
+            qx = q[0], qy = q[1], qz = q[2];
+        }
+        // padding rows (zero operand: every dt is 0) start at -inf so that nothing ever passes their filter
+        float mt = valid ? __int_as_float(0x7f800000) : __int_as_float(0xff800000);
+        float best = __int_as_float(0x7f800000);
+        int bidx = 0;
+        int cnt = 0;
+        const float rmax = __uint_as_float(*both.rmax_bits);
+        // |dt - d| <= eps; inputs too large for the bf16 split to stay finite disable the filter (eps = inf)
+        const float eps2 = (rmax < 1.0e15f) ? 2.0f * both.eps_scale * rmax * rmax : __int_as_float(0x7f800000);
+        const float *cb = a.cxyz + (size_t)bi * a.nc_full * 3;
+        const bool vec_ok = (((uintptr_t)cb) & 15u) == 0;
+        uint2 *evp = &S.ev[0][tid];
+
+        // exact re-evaluation of the listed blocks that are still inside the window
+        auto flush = [&]() {
+            const float thr = mt + eps2;
+            for (int e = 0; e < cnt; ++e) {
+                const uint2 ev = evp[(size_t)e * kScanThreads];
+                if (__uint_as_float(ev.y) > thr) continue;  // NaN counts as inside
+                const int j0 = (int)ev.x * 32;
+                auto cand = [&](int j, float cx, float cy, float cz) {
+                    const float d = sqdist_ref(qx, qy, qz, cx, cy, cz);
+                    if (j < a.nc && d < best) {  // ascending j + strict '<': lowest index among exact ties
+                        best = d;
+                        bidx = j;
+                    }
+                };
+                if (vec_ok && j0 + 32 <= a.nc_full) {
+                    const float4 *p = reinterpret_cast<const float4 *>(cb + (size_t)j0 * 3);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 u0 = __ldg(p + 3 * i), u1 = __ldg(p + 3 * i + 1), u2 = __ldg(p + 3 * i + 2);
+                        cand(j0 + 4 * i, u0.x, u0.y, u0.z);
+                        cand(j0 + 4 * i + 1, u0.w, u1.x, u1.y);
+                        cand(j0 + 4 * i + 2, u1.z, u1.w, u2.x);
+                        cand(j0 + 4 * i + 3, u2.y, u2.z, u2.w);
+                    }
+                } else {
+                    const int jend = min(j0 + 32, a.nc);
+                    for (int j = j0; j < jend; ++j) cand(j, __ldg(cb + (size_t)j * 3), __ldg(cb + (size_t)j * 3 + 1), __ldg(cb + (size_t)j * 3 + 2));
+                }
+            }
+            cnt = 0;
+        };
+
+        const unsigned tbase = tmem + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(g * kTileCols);
+        for (int t = 0; t < ntiles; ++t) {
+            mbar_wait(&S.full_bar[g], (unsigned)(t & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            unsigned v[64];
+            tmem_ld64_wait(v, tbase);
+            const float bm0 = tree_min32o(v, 0), bm1 = tree_min32o(v, 32);
+            tmem_ld64_wait(v, tbase + 64u);
+            // the values are in registers: hand the accumulator back to the tensor core
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.empty_bar[g]);
+            const float bm2 = tree_min32o(v, 0), bm3 = tree_min32o(v, 32);
+            mt = min3(mt, min3(bm0, bm1, bm2), bm3);
+            const float thr = mt + eps2;
+            const float bms[4] = {bm0, bm1, bm2, bm3};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (!(bms[i] > thr)) {  // predicated append
+                    evp[(size_t)cnt * kScanThreads] = make_uint2((unsigned)(t * 4 + i), __float_as_uint(bms[i]));
+                    ++cnt;
+                }
+            }
+            if (cnt > kEvCap - 4) flush();
+        }
+        flush();
+        if (valid) {
+            if (a.zero_if_pos && best > 0.0f) {
+                best = 0.0f;
+                bidx = 0;
+            }
+            const size_t off = (size_t)bi * a.nq + qrow;
+            if (a.dist) a.dist[off] = best;
+            a.idx[off] = bidx;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((unsigned)kScanTmemCols));
+}
+
 static size_t pad_rows(int cnt) { return ((size_t)cnt + kRowsPerCta - 1) / kRowsPerCta * kRowsPerCta; }
 
 size_t workspace_bytes(int b, int n, int m)
@@ -423,7 +665,13 @@ cudaError_t launch(int b, int n, const float *xyz1, int m, const float *xyz2, in
     {
         prof::Scope ps(st, prof::kChamferTwoWay);
         const size_t rows = np > mp ? np : mp;
-        search_kernel<<<dim3((unsigned)(rows / kRowsPerCta), b, 2), kThreads, 0, st>>>(s);
+        static const bool legacy = getenv("GEOM_TC_LEGACY") != nullptr;  // A/B switch: the inline-survivor kernel
+        if (legacy) {
+            search_kernel<<<dim3((unsigned)(rows / kRowsPerCta), b, 2), kThreads, 0, st>>>(s);
+        } else {
+            if ((e = cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem))) != cudaSuccess) return e;
+            scan_kernel<<<dim3((unsigned)(rows / kRowsPerCta), b, 2), kScanKernelThreads, sizeof(ScanSmem), st>>>(s);
+        }
     }
     return cudaGetLastError();
 }
