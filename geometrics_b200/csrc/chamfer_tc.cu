@@ -1,4 +1,4 @@
-// chamfer_tc.cu -- tensor-core FILTERED exact nearest-neighbour search (tcgen05 + TMEM), sm_100a.
+// chamfer_tc.cu -- tensor-core FILTERED exact nearest-neighbour search (tcgen05 + TMEM + TMA), sm_100a.
 //
 // Same results as the brute-force kernels of chamfer.cu (bit-identical distances and indices, lowest
 // index on ties), at a fraction of the FP32 work.  BASELINE's north_star allows tensor cores "if the
@@ -10,17 +10,26 @@
 //          dt(i,j) = |p_i|^2 + |q_j|^2 - 2 (ph.qh + pl.qh + ph.ql)            (fp32 accumulate)
 //      an approximation of the squared distance with |dt - d| <= eps, eps = kEpsScale * R^2,
 //      R = max |coordinate| of both point sets (derivation: DESIGN.md "Tensor-core filter").
-//   2. search_kernel: a CTA owns 256 query rows (two M=128 accumulators in TMEM) and streams
-//      128-candidate tiles: tcgen05.mma (one elected thread) -> tcgen05.ld -> every thread scans its
-//      row's 128 approximate distances with 3-input minima (0.5 instruction per pair).  Only
-//      candidates with  dt <= best_exact + eps  are re-evaluated with the reference's exact fp32
-//      sequence (sqdist_ref); the true nearest neighbour always passes this test because
-//      dt(j*) <= d(j*) + eps <= best_exact + eps.  Candidates are visited in ascending index order and
-//      replaced only on a strictly smaller exact distance, so ties resolve to the lowest index
-//      exactly as in the reference (chamfer_distance.cu:39,47).
+//      The packed operands are stored in the tensor core's shared-memory order (128-row blocks,
+//      k-chunk major), so a block is ONE contiguous 4 KB TMA bulk copy.
+//   2. scan_kernel: a CTA owns 4 x 128 query rows and streams 128-candidate tiles through a TMA ring.
+//      Row block g has two TMEM accumulators (64 candidates each), a producer warp that issues
+//      tcgen05.mma (M128 N64 K16) into whichever of the two is free, and four scanner warps (one per TMEM
+//      lane quarter) that pull 64 columns with tcgen05.ld, hand the accumulator back and reduce the
+//      values with 3-input minima (0.5 instruction per pair).  A thread owns one query row for the whole
+//      sweep.  No exact arithmetic inside the sweep: with mt = running minimum of dt for the row, a
+//      32-candidate block whose minimum bm satisfies bm <= mt + 2 eps is appended to the thread's EVENT
+//      list in shared memory (predicated store, no branch).  After the sweep (or when the list is nearly
+//      full) the thread re-evaluates, with the reference's exact fp32 sequence (sqdist_ref), every
+//      candidate of the listed blocks that still satisfy bm <= mt + 2 eps, in ascending index order
+//      with strict '<'.
+//      Correctness: the true nearest neighbour j* has dt(j*) <= d(j*) + eps <= d(jt) + eps <=
+//      dt(jt) + 2 eps = mt_final + 2 eps (jt = argmin dt); mt only decreases, so the block of j* is
+//      listed when it is scanned and survives every later re-check.  Candidates with the same exact
+//      distance as j* satisfy the same bound, so the lowest index among exact ties is found too
+//      (chamfer_distance.cu:39,47).
 //
-// One launch per direction (rows = queries), like the reference's two launches, but each launch costs
-// ~0.6 instructions per pair instead of ~10.
+// One launch covers both directions (blockIdx.z); ~0.9 instructions per pair instead of ~10.
 #include <cstdlib>
 
 #include <cuda_bf16.h>
@@ -30,11 +39,17 @@
 namespace geom {
 namespace chamfer_tc {
 
-constexpr int kRB = 4;                    // 128-row blocks per CTA (candidate-tile reuse factor)
-constexpr int kRowsPerCta = 128 * kRB;
-constexpr int kTileCols = 128;    // candidates per MMA
-constexpr int kThreads = 288;  // 8 scanner warps + 1 producer warp
-constexpr int kTmemCols = 2 * kTileCols;
+constexpr int kGroups = 4;                      // 128-row blocks per CTA == scanner warp groups
+constexpr int kRowsPerCta = 128 * kGroups;
+constexpr int kTileCols = 128;                  // candidates per ring stage (one packed block)
+constexpr int kHalfCols = 64;                   // candidates per MMA / accumulator
+constexpr int kScanThreads = kGroups * 128;     // warps 0-15: scanners
+constexpr int kThreads = kScanThreads + kGroups * 32;  // warps 16-19: one producer per group
+constexpr int kStages = 8;                      // candidate-tile ring (TMA)
+constexpr int kPrefetch = kStages - 2;          // tiles in flight ahead of the MMAs
+constexpr int kEvCap = 24;                      // events per thread held in shared memory
+constexpr int kTmemCols = kGroups * 2 * kHalfCols;
+constexpr unsigned kBlockBytes = 2 * 128 * 16;  // one packed 128-row block
 constexpr float kEpsScale = 2.5e-4f;
 constexpr float kBigNorm = 1.0e30f;  // padding candidates: approximate distance far above anything real
 
@@ -56,11 +71,12 @@ __device__ __forceinline__ unsigned short bf16_bits(float v) { return __bfloat16
 __device__ __forceinline__ float bf16_val(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 __device__ __forceinline__ unsigned pack_bf16x2(float lo, float hi) { return (unsigned)bf16_bits(lo) | ((unsigned)bf16_bits(hi) << 16); }
 
-// Per point: two 32-byte operand rows.
+// Per point: two 16-byte k-chunks per form.
 //   A form (query):      -2ph(3) -2pl(3) -2ph(3)  n1 n2 n3   1  1  1   0
 //   B form (candidate):    qh(3)   qh(3)   ql(3)   1  1  1   n1 n2 n3  0
 // Rows past `cnt` (padding up to a multiple of kRowsPerCta): A form zero.  Rows past `cnt_scan` (padding and
 // the reference's skipped tail): B form zero with n1 = kBigNorm, so they can never be a minimum.
+// Storage order (uint4 units): [batch item][128-row block][k-chunk][row in block].
 __global__ void __launch_bounds__(256)
 pack_kernel(int b, int cnt, int cnt_scan, int cnt_pad, const float *__restrict__ xyz, uint4 *__restrict__ formA,
             uint4 *__restrict__ formB, unsigned *__restrict__ rmax_bits)
@@ -89,10 +105,11 @@ pack_kernel(int b, int cnt, int cnt_scan, int cnt_pad, const float *__restrict__
             b0 = make_uint4(0, 0, 0, 0);
             b1 = make_uint4(0, 0, pack_bf16x2(kBigNorm, 0.f), 0);
         }
-        formA[t * 2] = a0;
-        formA[t * 2 + 1] = a1;
-        formB[t * 2] = b0;
-        formB[t * 2 + 1] = b1;
+        const size_t o = ((size_t)bi * cnt_pad + (size_t)(r & ~127)) * 2 + (size_t)(r & 127);
+        formA[o] = a0;
+        formA[o + 128] = a1;
+        formB[o] = b0;
+        formB[o + 128] = b1;
     }
     amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 16));
     amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 8));
@@ -105,8 +122,8 @@ pack_kernel(int b, int cnt, int cnt_scan, int cnt_pad, const float *__restrict__
 struct SearchArgs {
     const float *qxyz;    // exact query points   (b, nq, 3)
     const float *cxyz;    // exact candidates     (b, nc_full, 3)
-    const uint4 *formA;   // packed queries       (b, nq_pad, 2)
-    const uint4 *formB;   // packed candidates    (b, nc_pad, 2)
+    const uint4 *formA;   // packed queries       (b, nq_pad / 128 blocks)
+    const uint4 *formB;   // packed candidates    (b, nc_pad / 128 blocks)
     float *dist;          // (b, nq) or null
     int *idx;             // (b, nq)
     int nq, nq_pad, nc, nc_full, nc_pad;  // nc = scanned candidates (tail-trimmed), nc_full = array stride
@@ -118,28 +135,8 @@ struct SearchArgs2 {
     float eps_scale;      // kEpsScale (tests shrink it to measure the safety margin)
 };
 
-#define GEOM_TMEM_LD32(v, taddr)                                                                                      \
-    asm volatile(                                                                                                     \
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                     \
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                     \
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                     \
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), \
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),      \
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),     \
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                   \
-        : "r"(taddr))
-
-// tcgen05.wait::ld tied to the registers of the load it completes ("+r"), so that no use of those
-// registers can be scheduled above the wait.
-#define GEOM_TMEM_WAIT(v)                                                                                              \
-    asm volatile("tcgen05.wait::ld.sync.aligned;"                                                                      \
-                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),     \
-                   "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]),            \
-                   "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]),          \
-                   "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]),          \
-                   "+r"(v[29]), "+r"(v[30]), "+r"(v[31])::"memory")
-
-// 64 consecutive columns of this warp's 32 TMEM lanes, load and wait in ONE statement (no register ties needed)
+// 64 consecutive columns of this warp's 32 TMEM lanes: load and wait in ONE statement, so that no use of
+// the registers can be scheduled between the load and its wait.
 __device__ __forceinline__ void tmem_ld64_wait(unsigned (&v)[64], unsigned taddr)
 {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];\n\ttcgen05.wait::ld.sync.aligned;"
@@ -148,9 +145,9 @@ __device__ __forceinline__ void tmem_ld64_wait(unsigned (&v)[64], unsigned taddr
                  : "memory");
 }
 
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
 {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
 {
@@ -162,280 +159,31 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
                      : "memory");
     }
 }
-
 __device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-
-// A CTA owns kRB x 128 query rows and streams 128-candidate tiles.  Work unit gu = (pass, tile t, row block rb):
-// one M=128 x N=128 x K=16 MMA into accumulator gu&1 (double-buffered in TMEM).
-//   warp 8  (producer): cp.async of the candidate tiles, tcgen05.mma issue, tcgen05.commit -> full[gu&1]
-//   warps 0-7 (scanners): wait full -> tcgen05.ld (64 columns each) -> arrive empty[gu&1] -> scan registers.
-// No CTA-wide barrier in the steady state: the tensor core runs up to two units ahead of the scanners.
-// Scanner (warp w, lane l) owns row 32*(w&3)+l of each block and columns [64*(w>>2), +64) of each tile.
-__global__ void __launch_bounds__(kThreads, 2) search_kernel(const SearchArgs2 both)
+// TMA bulk copy global -> shared, completion counted in bytes on `bar`
+__device__ __forceinline__ void tma_load(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *bar)
 {
-    const SearchArgs &a = both.dir[blockIdx.z];
-    __shared__ __align__(128) uint4 sA[kRB][2][128];      // [row block][k-chunk][row]   canonical no-swizzle K-major
-    __shared__ __align__(128) uint4 sB[2][2][kTileCols];  // [buffer][k-chunk][row]
-    __shared__ __align__(16) float sX[4][kTileCols * 3];  // exact fp32 coordinates of the last four candidate tiles
-    __shared__ __align__(8) unsigned long long full_bar[2], empty_bar[2], x_bar[4];
-    __shared__ unsigned tmem_slot;
-    __shared__ float s_part[kRB][2][128];                 // per (row block, column half, row): partial minima
-    __shared__ int s_pidx[kRB][128];
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int bi = blockIdx.y;
-    const int row0 = blockIdx.x * kRowsPerCta;
-    if (row0 >= a.nq_pad) return;  // the grid covers the longer of the two directions
-    const int ntiles = (a.nc + kTileCols - 1) / kTileCols;
-
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"((unsigned)kTmemCols));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    if (tid == 0) {
-        for (int i = 0; i < 2; ++i) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&full_bar[i])), "r"(1u));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&empty_bar[i])), "r"(8u));
-        }
-        for (int i = 0; i < 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&x_bar[i])), "r"(32u));
-        asm volatile("fence.mbarrier_init.release.cluster;");
-    }
-    const uint4 *gB = a.formB + (size_t)bi * a.nc_pad * 2;
-    {
-        const uint4 *ga = a.formA + ((size_t)bi * a.nq_pad + row0) * 2;
-        for (int i = tid; i < kRowsPerCta * 2; i += kThreads) {
-            const int r = i >> 1;
-            cp_async16(&sA[r >> 7][i & 1][r & 127], &ga[i]);
-        }
-        cp_async_commit();
-        cp_async_wait_all();
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const unsigned tmem = tmem_slot;
-
-    if (warp == 8) {
-        // ================================ producer ================================
-        // D = f32, A = B = bf16, both K-major, N = 128, M = 128
-        const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(kTileCols >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
-        const float *cexact = a.cxyz + (size_t)bi * a.nc_full * 3;
-        auto load_tile = [&](int tile) {
-            // packed operands: 128 rows x 2 chunks = 256 16-byte copies, 8 per lane
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int c = lane + 32 * i;
-                cp_async16(&sB[tile & 1][c & 1][c >> 1], &gB[(size_t)tile * kTileCols * 2 + c]);
-            }
-            // exact coordinates: 384 floats, 12 per lane (4-byte copies: no alignment assumption on the caller's array)
-            const int last = a.nc_full * 3 - 1;
-#pragma unroll
-            for (int i = 0; i < 12; ++i) {
-                const int e = lane + 32 * i;
-                cp_async4(&sX[tile & 3][e], &cexact[min(tile * kTileCols * 3 + e, last)]);
-            }
-            cp_async_commit();
-        };
-        load_tile(0);
-        for (int ts = 0; ts < ntiles; ++ts) {
-            // this tile has landed (issued one tile ago): visible to the tensor core and to the scanners
-            cp_async_wait_all();
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_arrive(&x_bar[ts & 3]);
-            __syncwarp();
-            const int gu0 = ts * kRB;
-            if (ts + 1 < ntiles) {
-                // the other operand buffer was read by the MMAs of tile ts-1; the last of them is unit gu0-1.
-                // (sX[(ts+1)&3] was last used by tile ts-3, long retired: scanners lag the MMAs by < 2 units.)
-                if (gu0 > 0) mbar_wait(&full_bar[(gu0 - 1) & 1], (unsigned)(((gu0 - 1) >> 1) & 1));
-                load_tile(ts + 1);
-            }
-#pragma unroll
-            for (int rb = 0; rb < kRB; ++rb) {
-                const int gu = gu0 + rb;
-                // accumulator gu&1 was last read by the scanners of unit gu-2
-                if (gu >= 2) mbar_wait(&empty_bar[gu & 1], (unsigned)(((gu >> 1) - 1) & 1));
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (lane == 0) {
-                    const u64 da = make_desc(smem_u32(&sA[rb][0][0]), 128 * 16, 128);
-                    const u64 db = make_desc(smem_u32(&sB[ts & 1][0][0]), kTileCols * 16, 128);
-                    asm volatile(
-                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem + (unsigned)((gu & 1) * kTileCols)),
-                        "l"(da), "l"(db), "r"(idesc), "r"(0u)
-                        : "memory");
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&full_bar[gu & 1])) : "memory");
-                }
-                __syncwarp();
-            }
-        }
-    } else {
-        // ================================ scanners ================================
-        const int half = warp >> 2;               // column half of the tile this thread scans
-        const int rloc = (warp & 3) * 32 + lane;  // row inside a 128-row block == TMEM lane
-        float qx[kRB], qy[kRB], qz[kRB], mt[kRB], best[kRB];  // mt: running min of dt; best: exact distance so far
-        int bidx[kRB];
-#pragma unroll
-        for (int rb = 0; rb < kRB; ++rb) {
-            const int qrow = min(row0 + rb * 128 + rloc, a.nq - 1);
-            const float *q = a.qxyz + ((size_t)bi * a.nq + qrow) * 3;
-            qx[rb] = q[0], qy[rb] = q[1], qz[rb] = q[2];
-            // padding rows (zero operand: every dt is 0) start at -inf so that nothing ever passes their filter
-            mt[rb] = (row0 + rb * 128 + rloc < a.nq) ? __int_as_float(0x7f800000) : __int_as_float(0xff800000);
-            best[rb] = __int_as_float(0x7f800000);
-            bidx[rb] = 0;
-        }
-        const float rmax = __uint_as_float(*both.rmax_bits);
-        // |dt - d| <= eps; inputs too large for the bf16 split to stay finite disable the filter (eps = inf)
-        const float eps2 = (rmax < 1.0e15f) ? 2.0f * both.eps_scale * rmax * rmax : __int_as_float(0x7f800000);
-        // block minimum of 32 approximate distances with 3-input minima (0.5 instruction per pair)
-        auto block_min = [&](const unsigned(&v)[32]) {
-            float bm = min3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
-#pragma unroll
-            for (int k = 3; k + 1 < 32; k += 2) bm = min3(bm, __uint_as_float(v[k]), __uint_as_float(v[k + 1]));
-            return fminf(bm, __uint_as_float(v[31]));
-        };
-        // One sweep.  mt = running minimum of dt over the candidates seen so far (this block included); a
-        // candidate is re-evaluated exactly when dt <= mt + 2 eps.  The final survivors of a fixed-threshold
-        // filter {dt <= mt_final + 2 eps} are a subset (mt only decreases), and the true nearest neighbour
-        // j* is among them: dt(j*) <= d(j*) + eps <= d(jt) + eps <= dt(jt) + 2 eps = mt_final + 2 eps with
-        // jt = argmin dt.  Exact coordinates of the tile come from shared memory (staged by the producer).
-        for (int t = 0; t < ntiles; ++t) {
-            mbar_wait(&x_bar[t & 3], (unsigned)((t >> 2) & 1));
-            const float *xs = &sX[t & 3][half * 64 * 3];
-            const int c0 = t * kTileCols + half * 64;
-#pragma unroll
-            for (int rb = 0; rb < kRB; ++rb) {
-                const int gu = t * kRB + rb;
-                mbar_wait(&full_bar[gu & 1], (unsigned)((gu >> 1) & 1));
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const unsigned tbase = tmem + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)((gu & 1) * kTileCols + half * 64);
-                unsigned va[32], vb[32];
-                GEOM_TMEM_LD32(va, tbase);
-                GEOM_TMEM_LD32(vb, tbase + 32u);
-                GEOM_TMEM_WAIT(va);
-                GEOM_TMEM_WAIT(vb);
-                // the values are in registers: hand the accumulator back to the tensor core
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty_bar[gu & 1]);
-#pragma unroll
-                for (int hb = 0; hb < 2; ++hb) {
-                    const unsigned(&v)[32] = hb ? vb : va;
-                    const float bm = block_min(v);
-                    mt[rb] = fminf(mt[rb], bm);
-                    const float thr = mt[rb] + eps2;
-                    if (!(bm > thr)) {  // a candidate inside the window (NaN counts as inside)
-                        unsigned mask = 0;
-#pragma unroll
-                        for (int k = 0; k < 32; ++k) mask |= (!(__uint_as_float(v[k]) > thr)) ? (1u << k) : 0u;
-                        while (mask) {  // ascending index order
-                            const int k = hb * 32 + __ffs(mask) - 1;
-                            mask &= mask - 1;
-                            const int j = c0 + k;
-                            if (j < a.nc) {
-                                const float *cx = xs + k * 3;
-                                const float d = sqdist_ref(qx[rb], qy[rb], qz[rb], cx[0], cx[1], cx[2]);
-                                if (d < best[rb]) {  // ascending j + strict '<': lowest index among exact ties
-                                    best[rb] = d;
-                                    bidx[rb] = j;
-                                }
-                            }
-                        }
-                    }
-                }
-            }
-        }
-        float (&acc)[kRB] = best;
-        // merge the two column halves of every row: smaller exact distance, lower index on ties
-        if (half == 1) {
-#pragma unroll
-            for (int rb = 0; rb < kRB; ++rb) {
-                s_part[rb][1][rloc] = acc[rb];
-                s_pidx[rb][rloc] = bidx[rb];
-            }
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (half == 0) {
-#pragma unroll
-            for (int rb = 0; rb < kRB; ++rb) {
-                const int qrow = row0 + rb * 128 + rloc;
-                if (qrow >= a.nq) continue;
-                float best = acc[rb];
-                int bi_ = bidx[rb];
-                const float o = s_part[rb][1][rloc];
-                const int oi = s_pidx[rb][rloc];
-                if (o < best || (o == best && oi < bi_)) {
-                    best = o;
-                    bi_ = oi;
-                }
-                if (a.zero_if_pos && best > 0.0f) {
-                    best = 0.0f;
-                    bi_ = 0;
-                }
-                const size_t off = (size_t)bi * a.nq + qrow;
-                if (a.dist) a.dist[off] = best;
-                a.idx[off] = bi_;
-            }
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((unsigned)kTmemCols));
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
 }
 
-
-// ------------------------------------------------------------------------------------------------------
-// scan_kernel: the same filter with the survivor work DEFERRED, one accumulator per warp group.
-//
-// A CTA owns 4 x 128 query rows (A operands resident in shared memory) and streams 128-candidate tiles.
-// Row block g has its own TMEM accumulator (128 columns) and its own group of four scanner warps (one per
-// TMEM lane quarter), so a thread owns one query row for the whole sweep:
-//   warp 16 (producer): cp.async candidate tiles into a 4-stage ring; per tile and group: wait empty[g] ->
-//                       tcgen05.mma M128 N128 K16 -> tcgen05.commit -> full[g]
-//   warps 0-15 (scanners, g = warp>>2): wait full[g] -> tcgen05.ld 2 x 64 columns -> arrive empty[g] ->
-//                       minima of the four 32-candidate blocks with 3-input min trees (0.5 instr / pair).
-// No exact arithmetic inside the sweep.  With mt = running minimum of dt for the row, a block whose
-// minimum bm satisfies bm <= mt + 2 eps is appended to the thread's EVENT list (predicated store, no
-// branch).  After the sweep (or when the list is nearly full) the thread re-evaluates with the exact
-// fp32 sequence every candidate of the listed blocks that still satisfy bm <= mt + 2 eps, in ascending
-// index order with strict '<'.  Correctness: the true nearest neighbour j* has dt(j*) <= d(j*) + eps <=
-// d(jt) + eps <= dt(jt) + 2 eps = mt_final + 2 eps (jt = argmin dt), mt only decreases, so the block of j*
-// is listed when it is scanned and survives every later re-check; candidates with the same exact distance
-// as j* satisfy the same bound, so the lowest index among ties is found too.
-// ------------------------------------------------------------------------------------------------------
-constexpr int kGroups = 4;
-constexpr int kScanThreads = kGroups * 128;
-constexpr int kScanKernelThreads = kScanThreads + 32;
-constexpr int kStages = 4;   // candidate-tile ring
-constexpr int kEvCap = 24;   // events per thread held in shared memory
-constexpr int kScanTmemCols = kGroups * kTileCols;
 struct ScanSmem {
     uint4 sA[kGroups][2][128];           // [row block][k-chunk][row]  canonical no-swizzle K-major
     uint4 sB[kStages][2][kTileCols];     // [stage][k-chunk][row]
     uint2 ev[kEvCap][kScanThreads];      // (block index, block minimum of dt)
-    unsigned long long full_bar[kGroups], empty_bar[kGroups];
+    unsigned long long full_bar[kGroups][2], empty_bar[kGroups][2];  // accumulator hand-over, per group and half
+    unsigned long long b_full[kStages], b_free[kStages];             // ring stage landed / no longer read
+    unsigned long long a_full;
     unsigned tmem_slot;
 };
 
-// minimum of 32 approximate distances: 16 three-input minima as a depth-4 tree
-__device__ __forceinline__ float tree_min32(const unsigned (&v)[32])
-{
-    float l1[12];
-#pragma unroll
-    for (int i = 0; i < 10; ++i)
-        l1[i] = min3(__uint_as_float(v[3 * i]), __uint_as_float(v[3 * i + 1]), __uint_as_float(v[3 * i + 2]));
-    l1[10] = __uint_as_float(v[30]);
-    l1[11] = __uint_as_float(v[31]);
-    const float a0 = min3(l1[0], l1[1], l1[2]), a1 = min3(l1[3], l1[4], l1[5]);
-    const float a2 = min3(l1[6], l1[7], l1[8]), a3 = min3(l1[9], l1[10], l1[11]);
-    return fminf(min3(a0, a1, a2), a3);
-}
-__device__ __forceinline__ float tree_min32o(const unsigned (&v)[64], int o)
+// minimum of 32 approximate distances v[o..o+31]: 16 three-input minima as a depth-4 tree
+__device__ __forceinline__ float tree_min32(const unsigned (&v)[64], int o)
 {
     float l1[12];
 #pragma unroll
@@ -448,7 +196,7 @@ __device__ __forceinline__ float tree_min32o(const unsigned (&v)[64], int o)
     return fminf(min3(a0, a1, a2), a3);
 }
 
-__global__ void __launch_bounds__(kScanKernelThreads, 1) scan_kernel(const SearchArgs2 both)
+__global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 both)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     ScanSmem &S = *reinterpret_cast<ScanSmem *>(smem_raw);
@@ -458,76 +206,73 @@ __global__ void __launch_bounds__(kScanKernelThreads, 1) scan_kernel(const Searc
     const int row0 = blockIdx.x * kRowsPerCta;
     if (row0 >= a.nq_pad) return;  // the grid covers the longer of the two directions
     const int ntiles = (a.nc + kTileCols - 1) / kTileCols;
+    const uint4 *gB = a.formB + (size_t)bi * a.nc_pad * 2;
 
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_slot)), "r"((unsigned)kScanTmemCols));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_slot)), "r"((unsigned)kTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    if (tid == 0) {
-        for (int i = 0; i < kGroups; ++i) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&S.full_bar[i])), "r"(1u));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&S.empty_bar[i])), "r"(4u));
+    if (tid == kScanThreads) {
+        for (int g = 0; g < kGroups; ++g)
+            for (int h = 0; h < 2; ++h) {
+                mbar_init(&S.full_bar[g][h], 1);
+                mbar_init(&S.empty_bar[g][h], 4);
+            }
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&S.b_full[s], 1);
+            mbar_init(&S.b_free[s], kGroups);
         }
-        asm volatile("fence.mbarrier_init.release.cluster;");
+        mbar_init(&S.a_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // barrier words visible to the TMA unit
+        // the CTA's four packed query blocks are contiguous: one 16 KB copy; then the head of the candidate ring
+        tma_load(&S.sA[0][0][0], a.formA + ((size_t)bi * a.nq_pad + row0) * 2, kGroups * kBlockBytes, &S.a_full);
+        for (int t = 0; t < kPrefetch && t < ntiles; ++t)
+            tma_load(&S.sB[t][0][0], gB + (size_t)t * 256, kBlockBytes, &S.b_full[t]);
     }
-    const uint4 *gB = a.formB + (size_t)bi * a.nc_pad * 2;
-    {
-        const uint4 *ga = a.formA + ((size_t)bi * a.nq_pad + row0) * 2;
-        for (int i = tid; i < kRowsPerCta * 2; i += kScanKernelThreads) {
-            const int r = i >> 1;
-            cp_async16(&S.sA[r >> 7][i & 1][r & 127], &ga[i]);
-        }
-        cp_async_commit();
-        cp_async_wait_all();
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const unsigned tmem = S.tmem_slot;
 
-    if (warp == kGroups * 4) {
-        // ================================ producer ================================
-        const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(kTileCols >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
-        auto load_tile = [&](int tile) {
-            if (tile < ntiles) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {  // 128 rows x 2 chunks = 256 16-byte copies, 8 per lane
-                    const int c = lane + 32 * i;
-                    cp_async16(&S.sB[tile % kStages][c & 1][c >> 1], &gB[(size_t)tile * kTileCols * 2 + c]);
+    if (warp >= kGroups * 4) {
+        // ================================ producers (one warp per row block) ================================
+        const int g = warp - kGroups * 4;
+        // D = f32, A = B = bf16, both K-major, N = 64, M = 128
+        const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(kHalfCols >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
+        const u64 da = make_desc(smem_u32(&S.sA[g][0][0]), 128 * 16, 128);
+        mbar_wait(&S.a_full, 0);
+        for (int t = 0; t < ntiles; ++t) {
+            const int s = t % kStages;
+            if (g == 0) {
+                // ring refill: tile t+kPrefetch goes to the stage of tile t-2, once every group is done with it
+                const int tl = t + kPrefetch;
+                if (tl < ntiles) {
+                    if (t >= 2) mbar_wait(&S.b_free[tl % kStages], (unsigned)(((t - 2) / kStages) & 1));
+                    if (lane == 0) tma_load(&S.sB[tl % kStages][0][0], gB + (size_t)tl * 256, kBlockBytes, &S.b_full[tl % kStages]);
                 }
             }
-            cp_async_commit();  // always: keeps the group count uniform
-        };
-        load_tile(0);
-        load_tile(1);
-        for (int t = 0; t < ntiles; ++t) {
-            // stage (t+2)%4 was last read by the MMAs of tile t-2; those completed before the scanners could
-            // release the accumulators that the MMAs of tile t-1 (already issued) waited for.
-            load_tile(t + 2);
-            asm volatile("cp.async.wait_group 2;" ::: "memory");  // tile t has landed
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
+            mbar_wait(&S.b_full[s], (unsigned)((t / kStages) & 1));
 #pragma unroll
-            for (int g = 0; g < kGroups; ++g) {
-                if (t >= 1) mbar_wait(&S.empty_bar[g], (unsigned)((t - 1) & 1));
+            for (int h = 0; h < 2; ++h) {
+                // accumulator (g, h) was last read by the scanners of tile t-1
+                if (t >= 1) mbar_wait(&S.empty_bar[g][h], (unsigned)((t - 1) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (lane == 0) {
-                    const u64 da = make_desc(smem_u32(&S.sA[g][0][0]), 128 * 16, 128);
-                    const u64 db = make_desc(smem_u32(&S.sB[t % kStages][0][0]), kTileCols * 16, 128);
+                    const u64 db = make_desc(smem_u32(&S.sB[s][0][h * kHalfCols]), kTileCols * 16, 128);
                     asm volatile(
                         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem + (unsigned)(g * kTileCols)),
+                        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem + (unsigned)((g * 2 + h) * kHalfCols)),
                         "l"(da), "l"(db), "r"(idesc), "r"(0u)
                         : "memory");
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&S.full_bar[g])) : "memory");
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&S.full_bar[g][h])) : "memory");
                 }
                 __syncwarp();
             }
         }
     } else {
         // ================================ scanners ================================
-        const int g = warp >> 2;         // row block == accumulator == warp group
+        const int g = warp >> 2;                  // row block == warp group
         const int rloc = (warp & 3) * 32 + lane;  // row inside the block == TMEM lane
         const int qrow = row0 + g * 128 + rloc;
         const bool valid = qrow < a.nq;
@@ -580,26 +325,30 @@ __global__ void __launch_bounds__(kScanKernelThreads, 1) scan_kernel(const Searc
             cnt = 0;
         };
 
-        const unsigned tbase = tmem + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(g * kTileCols);
+        const unsigned tbase = tmem + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(g * 2 * kHalfCols);
         for (int t = 0; t < ntiles; ++t) {
-            mbar_wait(&S.full_bar[g], (unsigned)(t & 1));
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            unsigned v[64];
-            tmem_ld64_wait(v, tbase);
-            const float bm0 = tree_min32o(v, 0), bm1 = tree_min32o(v, 32);
-            tmem_ld64_wait(v, tbase + 64u);
-            // the values are in registers: hand the accumulator back to the tensor core
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&S.empty_bar[g]);
-            const float bm2 = tree_min32o(v, 0), bm3 = tree_min32o(v, 32);
-            mt = min3(mt, min3(bm0, bm1, bm2), bm3);
+            float bm[4];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                mbar_wait(&S.full_bar[g][h], (unsigned)(t & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                // both MMAs of this group on tile t are complete: the group no longer reads the ring stage
+                if (h == 1 && (warp & 3) == 0 && lane == 0) mbar_arrive(&S.b_free[t % kStages]);
+                unsigned v[64];
+                tmem_ld64_wait(v, tbase + (unsigned)(h * kHalfCols));
+                // the values are in registers: hand the accumulator back to the tensor core
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.empty_bar[g][h]);
+                bm[2 * h] = tree_min32(v, 0);
+                bm[2 * h + 1] = tree_min32(v, 32);
+            }
+            mt = min3(mt, min3(bm[0], bm[1], bm[2]), bm[3]);
             const float thr = mt + eps2;
-            const float bms[4] = {bm0, bm1, bm2, bm3};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                if (!(bms[i] > thr)) {  // predicated append
-                    evp[(size_t)cnt * kScanThreads] = make_uint2((unsigned)(t * 4 + i), __float_as_uint(bms[i]));
+                if (!(bm[i] > thr)) {  // predicated append
+                    evp[(size_t)cnt * kScanThreads] = make_uint2((unsigned)(t * 4 + i), __float_as_uint(bm[i]));
                     ++cnt;
                 }
             }
@@ -618,7 +367,7 @@ __global__ void __launch_bounds__(kScanKernelThreads, 1) scan_kernel(const Searc
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((unsigned)kScanTmemCols));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((unsigned)kTmemCols));
 }
 
 static size_t pad_rows(int cnt) { return ((size_t)cnt + kRowsPerCta - 1) / kRowsPerCta * kRowsPerCta; }
@@ -665,13 +414,8 @@ cudaError_t launch(int b, int n, const float *xyz1, int m, const float *xyz2, in
     {
         prof::Scope ps(st, prof::kChamferTwoWay);
         const size_t rows = np > mp ? np : mp;
-        static const bool legacy = getenv("GEOM_TC_LEGACY") != nullptr;  // A/B switch: the inline-survivor kernel
-        if (legacy) {
-            search_kernel<<<dim3((unsigned)(rows / kRowsPerCta), b, 2), kThreads, 0, st>>>(s);
-        } else {
-            if ((e = cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem))) != cudaSuccess) return e;
-            scan_kernel<<<dim3((unsigned)(rows / kRowsPerCta), b, 2), kScanKernelThreads, sizeof(ScanSmem), st>>>(s);
-        }
+        if ((e = cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem))) != cudaSuccess) return e;
+        scan_kernel<<<dim3((unsigned)(rows / kRowsPerCta), b, 2), kThreads, sizeof(ScanSmem), st>>>(s);
     }
     return cudaGetLastError();
 }
