@@ -229,19 +229,22 @@ def run_product(args):
 
     # ---- inputs: a ring of distinct sets (rank-dependent seeds), resident in HBM ----
     ring = []
-    ws_bytes = L.geom_chamfer_workspace_bytes(B, N_PTS, M_PTS)
+    fp32_path = args.path == "fp32"
+    flags = _lib.GEOM_FLAG_FP32 if fp32_path else 0
+    # the tensor-core filtered search is the library's choice whenever the workspace is large enough for it
+    ws_bytes = (L.geom_chamfer_workspace_bytes if fp32_path else L.geom_chamfer_tensor_workspace_bytes)(B, N_PTS, M_PTS)
     for r in range(RING):
         x1, x2 = _host_inputs(SEED + 7 * r + 100000 * rank)
         ring.append(dict(
             x1=x1.to(dev), x2=x2.to(dev),
             i1=torch.empty(B, N_PTS, dtype=torch.int32, device=dev), i2=torch.empty(B, M_PTS, dtype=torch.int32, device=dev),
-            ws=torch.empty(ws_bytes // 8, dtype=torch.int64, device=dev)))
+            ws=torch.empty((ws_bytes + 15) // 16 * 2, dtype=torch.int64, device=dev)))
 
     def step(k):
         s = ring[k % RING]
         # indices only, as chamfer_distance.py:31 returns (dist pointers NULL)
         st = L.geom_chamfer_fwd(B, N_PTS, s["x1"].data_ptr(), M_PTS, s["x2"].data_ptr(), None, s["i1"].data_ptr(),
-                                None, s["i2"].data_ptr(), s["ws"].data_ptr(), ws_bytes, 0, sp)
+                                None, s["i2"].data_ptr(), s["ws"].data_ptr(), ws_bytes, flags, sp)
         if st != 0:
             _lib.check(st, "geom_chamfer_fwd")
 
@@ -282,11 +285,12 @@ def run_product(args):
     hi2 = torch.empty(B, M_PTS, dtype=torch.int32).pin_memory()
     e2e_steps = max(3, min(args.steps, 30))
     for _ in range(2):
-        g.chamfer_forward_host(hx1, hx2, hi1, hi2, device=dev, chunks=args.e2e_chunks)
+        g.chamfer_forward_host(hx1, hx2, hi1, hi2, device=dev, chunks=args.e2e_chunks, tensor=False if fp32_path else None)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        g.chamfer_forward_host(hx1, hx2, hi1, hi2, device=dev, chunks=args.e2e_chunks)  # returns after the D2H copy completed
+        # returns after the D2H copy completed
+        g.chamfer_forward_host(hx1, hx2, hi1, hi2, device=dev, chunks=args.e2e_chunks, tensor=False if fp32_path else None)
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
 
@@ -315,12 +319,42 @@ def run_product(args):
         dom_ms = kern_ms_max
         ach = alg_bytes / (dom_ms * 1e-3) / 1e9
         sm_mhz = clocks.get("sm_mhz") or 1965
-        fp32_peak = 148 * 128 * sm_mhz * 1e6  # FP32 lane-ops/s at the clock observed under load
-        lane_ops = 6 * B * N_PTS * M_PTS      # 3 sub + 1 mul + 2 fma per pair, each pair evaluated once
+        hbm = {"achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "algorithmic_bytes": alg_bytes,
+               "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s"}
+        if "chamfer_tc" in dom_name:
+            # tensor-core filtered search: one M128 N64 K16 bf16 MMA per (128 query rows x 64 candidates), both
+            # directions, over the padded extents (rows to 512, candidates to 128); minima on the ALU pipe
+            pad = lambda v, q: (v + q - 1) // q * q
+            mma_flops = 2 * 16 * B * (pad(N_PTS, 512) * pad(M_PTS, 128) + pad(M_PTS, 512) * pad(N_PTS, 128))
+            tc_peak = float(peaks.get("bf16_tflops", 1650.0))
+            tc_ach = mma_flops / (dom_ms * 1e-3) / 1e12
+            alu_peak = 148 * 64 * sm_mhz * 1e6    # ALU pipe: 16 lanes x 4 SMSP per SM
+            alu_ops = B * N_PTS * M_PTS           # 3-input minimum: one lane-op per two approximate distances, two directions
+            roofline = {"bound": "tensor", "achieved": tc_ach, "peak": tc_peak, "unit": "TFLOP/s", "frac": tc_ach / tc_peak,
+                        "traffic": traffic, "traffic_source": traffic_src,
+                        "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1650 TFLOP/s",
+                        "kernel": dom_name, "kernel_ms": dom_ms, "flops_per_launch": mma_flops,
+                        "note": "flops = issued tcgen05.mma shapes (K=16 carries the 15-term split distance); the kernel is "
+                                "bound by the TMEM accumulator round trip and the ALU-pipe minima, not by HBM (see DESIGN.md 4.1)",
+                        "hbm": hbm,
+                        "alu": {"lane_ops_per_launch": alu_ops, "achieved_tlops": alu_ops / (dom_ms * 1e-3) / 1e12,
+                                "peak_tlops": alu_peak / 1e12, "frac": alu_ops / (dom_ms * 1e-3) / alu_peak,
+                                "peak_source": f"148 SM x 64 ALU lanes x {sm_mhz} MHz (median SM clock during the run)"}}
+        else:
+            fp32_peak = 148 * 128 * sm_mhz * 1e6  # FP32 lane-ops/s at the clock observed under load
+            lane_ops = 6 * B * N_PTS * M_PTS      # 3 sub + 1 mul + 2 fma per pair, each pair evaluated once
+            roofline = dict(hbm, bound="hbm", traffic=traffic, traffic_source=traffic_src, kernel=dom_name, kernel_ms=dom_ms,
+                            note="brute-force NN is FP32-issue bound, not HBM bound (SURVEY.md 8d); see fp32 below",
+                            fp32={"lane_ops_per_launch": lane_ops, "achieved_tlops": lane_ops / (dom_ms * 1e-3) / 1e12,
+                                  "peak_tlops": fp32_peak / 1e12, "frac": lane_ops / (dom_ms * 1e-3) / fp32_peak,
+                                  "peak_source": f"148 SM x 128 FP32 lanes x {sm_mhz} MHz (median SM clock during the run)"})
+        cfg = _config(world)
+        cfg["search_path"] = "CUDA-core packed-FP32 brute force (GEOM_FLAG_FP32)" if fp32_path else \
+            "tensor-core filtered exact search (tcgen05 bf16 filter + exact fp32 re-evaluation; library default)"
         out = {
             "metric": METRIC, "value": pairs_step / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": _config(world),
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
             "clocks": clocks,
             "e2e": {"value": pairs_step / e2e_s, "unit": UNIT, "h2d_bytes_per_step": hx1.numel() * 4 + hx2.numel() * 4,
                     "d2h_bytes_per_step": hi1.numel() * 4 + hi2.numel() * 4, "ms_per_step": e2e_s * 1e3,
@@ -328,13 +362,7 @@ def run_product(args):
             "gpu_launches": launches,
             "kernels": {k_: {"ms_per_launch": v[0] / v[1], "launches": v[1], "share_of_step": v[0] / args.steps / ms_step}
                         for k_, v in kern.items()},
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
-                         "kernel": dom_name, "kernel_ms": dom_ms, "algorithmic_bytes": alg_bytes,
-                         "note": "brute-force NN is FP32-issue bound, not HBM bound (SURVEY.md 8d); see fp32 below",
-                         "fp32": {"lane_ops_per_launch": lane_ops, "achieved_tlops": lane_ops / (dom_ms * 1e-3) / 1e12,
-                                  "peak_tlops": fp32_peak / 1e12, "frac": lane_ops / (dom_ms * 1e-3) / fp32_peak,
-                                  "peak_source": f"148 SM x 128 FP32 lanes x {sm_mhz} MHz (median SM clock during the run)"}},
+            "roofline": roofline,
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_block()
@@ -351,6 +379,7 @@ def main():
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-chunks", type=int, default=3, help="batch chunks pipelined by geom_chamfer_fwd_host")
+    ap.add_argument("--path", default="auto", choices=["auto", "fp32"], help="auto = library default (tensor-core filtered search); fp32 = CUDA-core brute force")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "product" else args.warmup
     if args.impl == "reference":

@@ -18,6 +18,7 @@ GEOM_FLAG_NONE = 0
 GEOM_FLAG_EXACT_TAIL = 1
 GEOM_FLAG_ONEWAY = 2
 GEOM_FLAG_TENSOR = 4
+GEOM_FLAG_FP32 = 8
 
 # every symbol include/geom_b200.h declares: name -> (restype, argtypes)
 _vp, _i, _u, _sz = C.c_void_p, C.c_int, C.c_uint, C.c_size_t
@@ -90,7 +91,7 @@ def lib() -> C.CDLL:
     return _lib
 
 
-GEOM_PROF_KERNELS = 16
+GEOM_PROF_KERNELS = 18
 
 
 def prof_begin() -> None:

@@ -15,8 +15,11 @@ from . import _lib
 
 
 def chamfer_forward(xyz1: torch.Tensor, xyz2: torch.Tensor, *, exact_tail: bool = False,
-                    oneway: bool = False, want_dist: bool = True, tensor: bool = False):
-    """-> (dist1, idx1, dist2, idx2); squared distances are fp32 (B,n)/(B,m) or None."""
+                    oneway: bool = False, want_dist: bool = True, tensor=None):
+    """-> (dist1, idx1, dist2, idx2); squared distances are fp32 (B,n)/(B,m) or None.
+
+    ``tensor``: None (default) lets the library choose (the tensor-core filtered search whenever the sizes
+    allow), True / False force the tensor-core / the CUDA-core search.  All paths return identical bits."""
     _lib.require_cuda_f32("xyz1", xyz1, 3)
     _lib.require_cuda_f32("xyz2", xyz2, 3)
     if xyz1.shape[0] != xyz2.shape[0]:
@@ -34,10 +37,11 @@ def chamfer_forward(xyz1: torch.Tensor, xyz2: torch.Tensor, *, exact_tail: bool 
         idx2 = torch.empty((b, m), dtype=torch.int32, device=dev)
         dist1 = torch.empty((b, n), dtype=torch.float32, device=dev) if want_dist else None
         dist2 = torch.empty((b, m), dtype=torch.float32, device=dev) if want_dist else None
-        ws_bytes = (L.geom_chamfer_tensor_workspace_bytes if tensor else L.geom_chamfer_workspace_bytes)(b, n, m)
+        fp32_only = tensor is False or oneway
+        ws_bytes = (L.geom_chamfer_workspace_bytes if fp32_only else L.geom_chamfer_tensor_workspace_bytes)(b, n, m)
         ws = torch.empty((max(ws_bytes, 16) + 15) // 16 * 2, dtype=torch.int64, device=dev)
         flags = (_lib.GEOM_FLAG_EXACT_TAIL if exact_tail else 0) | (_lib.GEOM_FLAG_ONEWAY if oneway else 0) \
-            | (_lib.GEOM_FLAG_TENSOR if tensor else 0)
+            | (_lib.GEOM_FLAG_TENSOR if tensor else 0) | (_lib.GEOM_FLAG_FP32 if tensor is False else 0)
         st = L.geom_chamfer_fwd(
             b, n, xyz1.data_ptr(), m, xyz2.data_ptr(),
             dist1.data_ptr() if want_dist else None, idx1.data_ptr(),
@@ -88,7 +92,8 @@ def _ctx_for(dev: torch.device):
 
 
 def chamfer_forward_host(xyz1: torch.Tensor, xyz2: torch.Tensor, idx1_out: torch.Tensor, idx2_out: torch.Tensor,
-                         device=None, chunks: int = 4, exact_tail: bool = False, dist1_out=None, dist2_out=None):
+                         device=None, chunks: int = 4, exact_tail: bool = False, dist1_out=None, dist2_out=None,
+                         tensor=None):
     """ChamferDistance on HOST tensors: ``xyz1`` (B,n,3) / ``xyz2`` (B,m,3) fp32 CPU tensors (pinned
     memory for full copy/compute overlap) -> ``idx1_out`` (B,n) / ``idx2_out`` (B,m) int32 CPU tensors
     (and optionally the squared distances).
@@ -123,6 +128,7 @@ def chamfer_forward_host(xyz1: torch.Tensor, xyz2: torch.Tensor, idx1_out: torch
         rc = L.geom_chamfer_fwd_host(_ctx_for(dev), b, n, xyz1.data_ptr(), m, xyz2.data_ptr(),
                                      dist1_out.data_ptr() if dist1_out is not None else None, idx1_out.data_ptr(),
                                      dist2_out.data_ptr() if dist2_out is not None else None, idx2_out.data_ptr(),
-                                     int(chunks), _lib.GEOM_FLAG_EXACT_TAIL if exact_tail else 0)
+                                     int(chunks), (_lib.GEOM_FLAG_EXACT_TAIL if exact_tail else 0)
+                                     | (_lib.GEOM_FLAG_TENSOR if tensor else 0) | (_lib.GEOM_FLAG_FP32 if tensor is False else 0))
     _lib.check(rc, "geom_chamfer_fwd_host")
     return idx1_out, idx2_out

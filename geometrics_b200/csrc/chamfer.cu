@@ -536,9 +536,13 @@ extern "C" int geom_chamfer_fwd(int b, int n, const float *xyz1, int m, const fl
     const int zero2 = (!exact && (n % kRefTile) >= 1 && (n % kRefTile) <= 3) ? 1 : 0;
 
     cudaError_t e = cudaSuccess;
-    if ((flags & GEOM_FLAG_TENSOR) && !(flags & GEOM_FLAG_ONEWAY) && n_scan > 0 && m_scan > 0 && b <= 65535) {
-        const size_t need = geom_chamfer_tensor_workspace_bytes(b, n, m);
-        if (!workspace || workspace_bytes < need || ((uintptr_t)workspace & 15u)) return GEOM_ERR_WORKSPACE;
+    // Path choice: GEOM_FLAG_FP32 / GEOM_FLAG_ONEWAY force the CUDA-core kernels, GEOM_FLAG_TENSOR the tensor-core
+    // filtered search; with neither, the tensor-core search runs whenever the caller's workspace is large enough.
+    const bool tc_possible = !(flags & (GEOM_FLAG_ONEWAY | GEOM_FLAG_FP32)) && n_scan > 0 && m_scan > 0 && b <= 65535;
+    const size_t tc_need = tc_possible ? geom_chamfer_tensor_workspace_bytes(b, n, m) : 0;
+    const bool tc_fits = workspace && workspace_bytes >= tc_need && !((uintptr_t)workspace & 15u);
+    if (tc_possible && ((flags & GEOM_FLAG_TENSOR) || tc_fits)) {
+        if (!tc_fits) return GEOM_ERR_WORKSPACE;
         return status_from_cuda(chamfer_tc::launch(b, n, xyz1, m, xyz2, n_scan, m_scan, zero1, zero2, dist1, idx1, dist2,
                                                    idx2, workspace, st));
     }

@@ -47,7 +47,7 @@ constexpr int kScanThreads = kGroups * 128;     // warps 0-15: scanners
 constexpr int kThreads = kScanThreads + kGroups * 32;  // warps 16-19: one producer per group
 constexpr int kStages = 8;                      // candidate-tile ring (TMA)
 constexpr int kPrefetch = kStages - 2;          // tiles in flight ahead of the MMAs
-constexpr int kEvCap = 24;                      // events per thread held in shared memory
+constexpr int kEvCap = 16;                      // events (listed tiles) per thread held in shared memory
 constexpr int kTmemCols = kGroups * 2 * kHalfCols;
 constexpr unsigned kBlockBytes = 2 * 128 * 16;  // one packed 128-row block
 constexpr float kEpsScale = 2.5e-4f;
@@ -175,7 +175,8 @@ __device__ __forceinline__ void tma_load(void *smem_dst, const void *gmem_src, u
 struct ScanSmem {
     uint4 sA[kGroups][2][128];           // [row block][k-chunk][row]  canonical no-swizzle K-major
     uint4 sB[kStages][2][kTileCols];     // [stage][k-chunk][row]
-    uint2 ev[kEvCap][kScanThreads];      // (block index, block minimum of dt)
+    float4 evm[kEvCap][kScanThreads];    // events: the four 32-candidate block minima of a listed tile ...
+    unsigned evt[kEvCap][kScanThreads];  // ... and the tile index
     unsigned long long full_bar[kGroups][2], empty_bar[kGroups][2];  // accumulator hand-over, per group and half
     unsigned long long b_full[kStages], b_free[kStages];             // ring stage landed / no longer read
     unsigned long long a_full;
@@ -291,15 +292,33 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 bot
         const float eps2 = (rmax < 1.0e15f) ? 2.0f * both.eps_scale * rmax * rmax : __int_as_float(0x7f800000);
         const float *cb = a.cxyz + (size_t)bi * a.nc_full * 3;
         const bool vec_ok = (((uintptr_t)cb) & 15u) == 0;
-        uint2 *evp = &S.ev[0][tid];
+        float4 *evm = &S.evm[0][tid];
+        unsigned *evt = &S.evt[0][tid];
 
-        // exact re-evaluation of the listed blocks that are still inside the window
+        // Exact re-evaluation of the listed tiles' 32-candidate blocks that are still inside the window.
+        // Pass 1 compacts the thread's surviving blocks to the front of its list (in place: at most four
+        // block ids per event, written behind the read position), so that pass 2 runs
+        // max-over-lanes(survivors) block evaluations per warp.
         auto flush = [&]() {
             const float thr = mt + eps2;
+            unsigned *blk = reinterpret_cast<unsigned *>(&S.evm[0][0]);  // survivors: reuse evm[e][tid] as 4 x u32
+            int keep = 0;
             for (int e = 0; e < cnt; ++e) {
-                const uint2 ev = evp[(size_t)e * kScanThreads];
-                if (__uint_as_float(ev.y) > thr) continue;  // NaN counts as inside
-                const int j0 = (int)ev.x * 32;
+                const float4 m = evm[(size_t)e * kScanThreads];
+                const unsigned t4 = evt[(size_t)e * kScanThreads] * 4u;
+                // block ids of event e are written into evm[keep >> 2]: keep <= 4 e before the event, and
+                // event e has already been read, so slot (keep >> 2) <= e is free to overwrite
+                const float bms[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (!(bms[i] > thr)) {  // NaN counts as inside
+                        blk[((size_t)(keep >> 2) * kScanThreads + tid) * 4 + (keep & 3)] = t4 + i;
+                        ++keep;
+                    }
+                }
+            }
+            for (int e = 0; e < keep; ++e) {
+                const int j0 = (int)blk[((size_t)(e >> 2) * kScanThreads + tid) * 4 + (e & 3)] * 32;
                 auto cand = [&](int j, float cx, float cy, float cz) {
                     const float d = sqdist_ref(qx, qy, qz, cx, cy, cz);
                     if (j < a.nc && d < best) {  // ascending j + strict '<': lowest index among exact ties
@@ -326,33 +345,44 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 bot
         };
 
         const unsigned tbase = tmem + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(g * 2 * kHalfCols);
+        const unsigned bfree0 = smem_u32(&S.b_free[0]);
+        const bool group_leader = (warp & 3) == 0 && lane == 0;
         for (int t = 0; t < ntiles; ++t) {
-            float bm[4];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                mbar_wait(&S.full_bar[g][h], (unsigned)(t & 1));
+            float bm0, bm1, bm2, bm3;
+            {
+                mbar_wait(&S.full_bar[g][0], (unsigned)(t & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                // both MMAs of this group on tile t are complete: the group no longer reads the ring stage
-                if (h == 1 && (warp & 3) == 0 && lane == 0) mbar_arrive(&S.b_free[t % kStages]);
                 unsigned v[64];
-                tmem_ld64_wait(v, tbase + (unsigned)(h * kHalfCols));
+                tmem_ld64_wait(v, tbase);
                 // the values are in registers: hand the accumulator back to the tensor core
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&S.empty_bar[g][h]);
-                bm[2 * h] = tree_min32(v, 0);
-                bm[2 * h + 1] = tree_min32(v, 32);
+                if (lane == 0) mbar_arrive(&S.empty_bar[g][0]);
+                bm0 = tree_min32(v, 0);
+                bm1 = tree_min32(v, 32);
             }
-            mt = min3(mt, min3(bm[0], bm[1], bm[2]), bm[3]);
-            const float thr = mt + eps2;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (!(bm[i] > thr)) {  // predicated append
-                    evp[(size_t)cnt * kScanThreads] = make_uint2((unsigned)(t * 4 + i), __float_as_uint(bm[i]));
-                    ++cnt;
-                }
+            {
+                mbar_wait(&S.full_bar[g][1], (unsigned)(t & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                // both MMAs of this group on tile t are complete: the group no longer reads the ring stage
+                if (group_leader) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bfree0 + 8u * (unsigned)(t % kStages)) : "memory");
+                unsigned v[64];
+                tmem_ld64_wait(v, tbase + (unsigned)kHalfCols);
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.empty_bar[g][1]);
+                bm2 = tree_min32(v, 0);
+                bm3 = tree_min32(v, 32);
             }
-            if (cnt > kEvCap - 4) flush();
+            const float m4 = min3(min3(bm0, bm1, bm2), bm3, mt);
+            mt = m4;
+            const float tm = fminf(fminf(bm0, bm1), fminf(bm2, bm3));
+            if (!(tm > mt + eps2)) {  // predicated append: the tile holds a candidate inside the window
+                evm[(size_t)cnt * kScanThreads] = make_float4(bm0, bm1, bm2, bm3);
+                evt[(size_t)cnt * kScanThreads] = (unsigned)t;
+                ++cnt;
+            }
+            if (cnt >= kEvCap) flush();
         }
         flush();
         if (valid) {
@@ -393,7 +423,7 @@ cudaError_t launch(int b, int n, const float *xyz1, int m, const float *xyz2, in
     cudaError_t e = cudaMemsetAsync(rmax, 0, 256, st);
     if (e != cudaSuccess) return e;
     {
-        prof::Scope ps(st, prof::kMisc2);
+        prof::Scope ps(st, prof::kChamferTcPack);
         pack_kernel<<<(unsigned)(((size_t)b * np + 255) / 256), 256, 0, st>>>(b, n, n_scan, (int)np, xyz1, a1, b1, rmax);
         pack_kernel<<<(unsigned)(((size_t)b * mp + 255) / 256), 256, 0, st>>>(b, m, m_scan, (int)mp, xyz2, a2, b2, rmax);
     }
@@ -412,7 +442,7 @@ cudaError_t launch(int b, int n, const float *xyz1, int m, const float *xyz2, in
     d1.qxyz = xyz2, d1.cxyz = xyz1, d1.formA = a2, d1.formB = b1, d1.dist = dist2, d1.idx = idx2;
     d1.nq = m, d1.nq_pad = (int)mp, d1.nc = n_scan, d1.nc_full = n, d1.nc_pad = (int)np, d1.zero_if_pos = zero2;
     {
-        prof::Scope ps(st, prof::kChamferTwoWay);
+        prof::Scope ps(st, prof::kChamferTcScan);
         const size_t rows = np > mp ? np : mp;
         if ((e = cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem))) != cudaSuccess) return e;
         scan_kernel<<<dim3((unsigned)(rows / kRowsPerCta), b, 2), kThreads, sizeof(ScanSmem), st>>>(s);

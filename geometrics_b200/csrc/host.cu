@@ -100,7 +100,8 @@ extern "C" int geom_chamfer_fwd_host(geom_host_ctx *c, int b, int n, const float
     const size_t s_x1 = align_up(sizeof(float) * 3 * (size_t)b * n, 256), s_x2 = align_up(sizeof(float) * 3 * (size_t)b * m, 256);
     const size_t s_i1 = align_up(sizeof(int) * (size_t)b * n, 256), s_i2 = align_up(sizeof(int) * (size_t)b * m, 256);
     const size_t s_d1 = h_dist1 ? s_i1 : 0, s_d2 = h_dist2 ? s_i2 : 0;
-    const size_t ws_one = align_up(geom_chamfer_workspace_bytes(per, n, m), 256);
+    const bool cuda_cores = (flags & (GEOM_FLAG_FP32 | GEOM_FLAG_ONEWAY)) != 0;
+    const size_t ws_one = align_up(cuda_cores ? geom_chamfer_workspace_bytes(per, n, m) : geom_chamfer_tensor_workspace_bytes(per, n, m), 256);
     cudaError_t e = ensure_arena(c, s_x1 + s_x2 + s_i1 + s_i2 + s_d1 + s_d2 + ws_one * chunks);
     if (e != cudaSuccess) return geom::status_from_cuda(e);
     char *base = (char *)c->arena;

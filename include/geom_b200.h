@@ -51,8 +51,13 @@ typedef void *geom_stream_t; /* cudaStream_t */
 /* Chamfer only: use the simple one-direction-at-a-time kernel instead of the fused two-way one. */
 #define GEOM_FLAG_ONEWAY 2u
 /* Chamfer only: tensor-core filtered exact search (tcgen05 bf16 contraction as a conservative filter,
- * exact fp32 re-evaluation of the survivors); same results, bit for bit. */
+ * exact fp32 re-evaluation of the survivors); same results, bit for bit.  Needs a workspace of
+ * geom_chamfer_tensor_workspace_bytes().  With neither GEOM_FLAG_TENSOR nor GEOM_FLAG_FP32 the library picks:
+ * the tensor-core search when the workspace passed is large enough for it (and the sizes allow), the
+ * CUDA-core search otherwise. */
 #define GEOM_FLAG_TENSOR 4u
+/* Chamfer only: force the CUDA-core (packed FP32) brute-force search. */
+#define GEOM_FLAG_FP32 8u
 
 GEOM_API int geom_abi_version(void);
 /* Static string for a status returned by any geom_* call. */
@@ -65,7 +70,7 @@ GEOM_API int geom_device_info(int *sm_count, int *cc_major, int *cc_minor);
  * the API is bracketed by CUDA events on its launch stream; geom_prof_end() synchronises on them and
  * returns, per kernel id, the summed device milliseconds and the launch count (arrays of
  * GEOM_PROF_KERNELS entries, either may be NULL).  Used by bench.py for the roofline figures. */
-#define GEOM_PROF_KERNELS 16
+#define GEOM_PROF_KERNELS 18
 GEOM_API int geom_prof_begin(void);
 GEOM_API int geom_prof_end(float *ms_per_kernel, int *launches_per_kernel);
 GEOM_API const char *geom_prof_kernel_name(int id);
@@ -82,7 +87,8 @@ GEOM_API const char *geom_prof_kernel_name(int id);
  * Inputs must be finite.
  * ------------------------------------------------------------------------------------------- */
 GEOM_API size_t geom_chamfer_workspace_bytes(int b, int n, int m);
-/* workspace needed when GEOM_FLAG_TENSOR is set (packed bf16 operands: 64 B per padded point); 16-byte aligned */
+/* workspace for the tensor-core search (packed bf16 operands: 64 B per padded point; >= the plain workspace);
+ * 16-byte aligned.  Passing a workspace of this size lets flags = 0 select the tensor-core search. */
 GEOM_API size_t geom_chamfer_tensor_workspace_bytes(int b, int n, int m);
 GEOM_API int geom_chamfer_fwd(int b, int n, const float *xyz1, int m, const float *xyz2,
                      float *dist1, int *idx1, float *dist2, int *idx2,

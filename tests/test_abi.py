@@ -15,6 +15,17 @@ def _declared_symbols():
     return sorted(set(re.findall(r"GEOM_API[^;]*?\b(geom_\w+)\s*\(", text)))
 
 
+def test_header_constants_mirrored():
+    """Numeric constants the ctypes layer duplicates must match the header."""
+    import re
+    from geometrics_b200 import _lib
+
+    text = open(os.path.join(ROOT, "include", "geom_b200.h")).read()
+    consts = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define (GEOM_[A-Z0-9_]+) (\d+)u?\b", text)}
+    for name in ("GEOM_PROF_KERNELS", "GEOM_FLAG_EXACT_TAIL", "GEOM_FLAG_ONEWAY", "GEOM_FLAG_TENSOR", "GEOM_FLAG_FP32"):
+        assert getattr(_lib, name) == consts[name], name
+
+
 def test_header_symbols_exported():
     from geometrics_b200 import _lib
 

@@ -10,7 +10,8 @@ from helpers import CHAMFER_CASES, chamfer_inputs, assert_same_f32
 
 pytestmark = pytest.mark.gpu
 
-MODES = [dict(), dict(oneway=True), dict(exact_tail=True), dict(exact_tail=True, oneway=True)]
+MODES = [dict(), dict(oneway=True), dict(exact_tail=True), dict(exact_tail=True, oneway=True),
+         dict(tensor=False), dict(tensor=False, exact_tail=True)]  # default = library choice (tensor-core search)
 _ids = lambda c: f"{c[0]}-{c[1]}x{c[2]}x{c[3]}"  # noqa: E731
 
 
@@ -216,10 +217,11 @@ def test_tensor_path_full_size_and_ranges(cuda, scale, offset):
     for mk in (synth.random_points, lambda b_, n_, s_: synth.lattice_points(b_, n_, 64, s_)):
         x1 = (mk(b, 10000, 41) * scale + offset).to(cuda)
         x2 = (mk(b, 10000, 42) * scale + offset).to(cuda)
-        want = g.chamfer_forward(x1, x2)
+        want = g.chamfer_forward(x1, x2, tensor=False)
         got = g.chamfer_forward(x1, x2, tensor=True)
-        for a_, b_ in zip(got, want):
-            assert torch.equal(a_, b_)
+        auto = g.chamfer_forward(x1, x2)
+        for a_, b_, c_ in zip(got, want, auto):
+            assert torch.equal(a_, b_) and torch.equal(c_, b_)
 
 
 def test_tensor_path_margin(cuda, monkeypatch):
@@ -228,7 +230,7 @@ def test_tensor_path_margin(cuda, monkeypatch):
     import geometrics_b200 as g
 
     x1, x2 = synth.random_points(8, 10000, 3).to(cuda), synth.random_points(8, 10000, 4).to(cuda)
-    want = g.chamfer_forward(x1, x2)
+    want = g.chamfer_forward(x1, x2, tensor=False)
     monkeypatch.setenv("GEOM_TC_EPS_SCALE", "0.125")
     got = g.chamfer_forward(x1, x2, tensor=True)
     for a_, b_ in zip(got, want):

@@ -17,7 +17,7 @@ what = sys.argv[1] if len(sys.argv) > 1 else "chamfer"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 if what == "chamfer":
     a, b = synth.random_points(32, 10000, 41).to(dev), synth.random_points(32, 10000, 1041).to(dev)
-    fn = lambda: g.chamfer_forward(a, b, want_dist=False, tensor=bool(os.environ.get("GEOM_BENCH_TENSOR")))
+    fn = lambda: g.chamfer_forward(a, b, want_dist=False, tensor=False if os.environ.get("GEOM_BENCH_FP32") else None)
 elif what == "tri":
     v, f = synth.uv_sphere(50, 50)
     t1, t2, t3 = (t.to(dev) for t in synth.face_vertices(synth.mesh_batch(v, 32), f))

@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(128) mma_rate(const __nv_bfloat16 *A, const __
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5;
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(256u));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     if (tid == 0) {
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(128) mma_rate(const __nv_bfloat16 *A, const __
             asm volatile(
                 "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                ::"r"(tmem + (uint32_t)((r & 1) * 128 * (NCOLS <= 128))), "l"(da), "l"(db), "r"(idesc), "r"(0u) : "memory");
+                ::"r"(tmem + (uint32_t)((r % (512 / NCOLS)) * NCOLS)), "l"(da), "l"(db), "r"(idesc), "r"(0u) : "memory");
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
     }
     {
@@ -144,7 +144,54 @@ __global__ void __launch_bounds__(128) mma_rate(const __nv_bfloat16 *A, const __
     if (tid == 0) { t1 = clock64(); cycles[blockIdx.x] = t1 - t0; }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
+}
+
+// latency: one MMA -> commit -> mbarrier wait, serialised REPS times by the issuing thread; cycles per round
+template <int NCOLS>
+__global__ void __launch_bounds__(128) mma_latency(const __nv_bfloat16 *A, const __nv_bfloat16 *B, long long *cycles, int reps)
+{
+    __shared__ __align__(128) uint4 sA[2][M_];
+    __shared__ __align__(128) uint4 sB[2][N_];
+    __shared__ __align__(8) unsigned long long bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar)), "r"(1u));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    for (int i = tid; i < M_ * 2; i += 128) sA[i & 1][i >> 1] = reinterpret_cast<const uint4 *>(A)[i];
+    for (int i = tid; i < N_ * 2; i += 128) sB[i & 1][i >> 1] = reinterpret_cast<const uint4 *>(B)[i];
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+    if (tid == 0) {
+        const uint64_t da = make_desc(smem_u32(&sA[0][0]), M_ * 16, 128);
+        const uint64_t db = make_desc(smem_u32(&sB[0][0]), N_ * 16, 128);
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NCOLS >> 3) << 17) | ((uint32_t)(M_ >> 4) << 24);
+        const long long t0 = clock64();
+        for (int r = 0; r < reps; ++r) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(0u) : "memory");
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+            uint32_t done = 0;
+            while (!done)
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done) : "r"(smem_u32(&bar)), "r"((uint32_t)(r & 1)) : "memory");
+        }
+        cycles[blockIdx.x] = clock64() - t0;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
 }
 
 // pipeline probe: 1 producer warp + 8 scanner warps, double-buffered 128-column accumulators, no real
@@ -270,14 +317,23 @@ int main()
     }
     long long *dc; cudaMalloc(&dc, 8 * 296);
     for (int blocks : {1, 148, 296}) {
-        for (int ncols : {128, 256}) {
+        for (int ncols : {32, 64, 128, 256}) {
             const int reps = 2000;
-            if (ncols == 128) mma_rate<128><<<blocks, 128>>>(dA, dB, dc, reps); else mma_rate<256><<<blocks, 128>>>(dA, dB, dc, reps);
+            if (ncols == 32) mma_rate<32><<<blocks, 128>>>(dA, dB, dc, reps);
+            else if (ncols == 64) mma_rate<64><<<blocks, 128>>>(dA, dB, dc, reps);
+            else if (ncols == 128) mma_rate<128><<<blocks, 128>>>(dA, dB, dc, reps); else mma_rate<256><<<blocks, 128>>>(dA, dB, dc, reps);
             cudaError_t e = cudaDeviceSynchronize();
             long long hc[296]; cudaMemcpy(hc, dc, 8 * blocks, cudaMemcpyDeviceToHost);
             printf("MMA M=128 N=%d K=16 bf16, %d CTAs: %s  %.1f cycles per MMA (CTA 0), %.0f flop/clk/CTA\n", ncols, blocks, cudaGetErrorString(e),
                    (double)hc[0] / reps, 2.0 * 128 * ncols * 16 / ((double)hc[0] / reps));
         }
+    }
+    for (int ncols : {64, 128}) {
+        const int reps = 1000;
+        if (ncols == 64) mma_latency<64><<<148, 128>>>(dA, dB, dc, reps); else mma_latency<128><<<148, 128>>>(dA, dB, dc, reps);
+        cudaError_t e = cudaDeviceSynchronize();
+        long long hc[148]; cudaMemcpy(hc, dc, 8 * 148, cudaMemcpyDeviceToHost);
+        printf("MMA latency M=128 N=%d K=16: %s  %.1f cycles per (mma -> commit -> mbarrier wait) round\n", ncols, cudaGetErrorString(e), (double)hc[0] / reps);
     }
     float *sink; cudaMalloc(&sink, 4 * 288);
     {
