@@ -378,7 +378,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-chunks", type=int, default=3, help="batch chunks pipelined by geom_chamfer_fwd_host")
+    ap.add_argument("--e2e-chunks", type=int, default=5, help="batch chunks pipelined by geom_chamfer_fwd_host")
     ap.add_argument("--path", default="auto", choices=["auto", "fp32"], help="auto = library default (tensor-core filtered search); fp32 = CUDA-core brute force")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "product" else args.warmup

@@ -408,6 +408,12 @@ size_t workspace_bytes(int b, int n, int m)
     return ((size_t)b * (pad_rows(n) + pad_rows(m)) * 2) * 32 + 256;
 }
 
+int ctas_per_item(int n, int m)
+{
+    const size_t np = pad_rows(n), mp = pad_rows(m);
+    return (int)(2 * ((np > mp ? np : mp) / kRowsPerCta));
+}
+
 // Both directions.  n_scan / m_scan: candidates actually scanned (reference tail skip); zero1 / zero2: the
 // reference's empty-final-tile behaviour.  Requires n_scan > 0 and m_scan > 0.
 cudaError_t launch(int b, int n, const float *xyz1, int m, const float *xyz2, int n_scan, int m_scan, int zero1,
@@ -444,7 +450,13 @@ cudaError_t launch(int b, int n, const float *xyz1, int m, const float *xyz2, in
     {
         prof::Scope ps(st, prof::kChamferTcScan);
         const size_t rows = np > mp ? np : mp;
-        if ((e = cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem))) != cudaSuccess) return e;
+        static bool smem_set[64] = {};  // per device: opt in to > 48 KB of dynamic shared memory once
+        int dev = 0;
+        if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+        if (dev < 0 || dev >= 64 || !smem_set[dev]) {
+            if ((e = cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem))) != cudaSuccess) return e;
+            if (dev >= 0 && dev < 64) smem_set[dev] = true;
+        }
         scan_kernel<<<dim3((unsigned)(rows / kRowsPerCta), b, 2), kThreads, sizeof(ScanSmem), st>>>(s);
     }
     return cudaGetLastError();

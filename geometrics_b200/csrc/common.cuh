@@ -130,6 +130,7 @@ struct Scope {
 // tensor-core filtered Chamfer search (chamfer_tc.cu)
 namespace chamfer_tc {
 size_t workspace_bytes(int b, int n, int m);
+int ctas_per_item(int n, int m);  // thread blocks one batch item contributes to the search grid (one CTA per SM)
 cudaError_t launch(int b, int n, const float *xyz1, int m, const float *xyz2, int n_scan, int m_scan, int zero1,
                    int zero2, float *dist1, int *idx1, float *dist2, int *idx2, void *workspace, cudaStream_t st);
 }  // namespace chamfer_tc

@@ -84,7 +84,25 @@ extern "C" int geom_chamfer_fwd_host(geom_host_ctx *c, int b, int n, const float
     // Slice boundaries: small first and last slices (only the first copy-in and the last copy-out are
     // exposed), the rest split evenly.  lo[k]..lo[k+1] is slice k.
     int lo_of[geom_host_ctx::kMaxChunks + 1];
-    {
+    const bool cuda_cores = (flags & (GEOM_FLAG_FP32 | GEOM_FLAG_ONEWAY)) != 0;
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device) != cudaSuccess) sms = 0;
+    const int per_item = cuda_cores ? 0 : geom::chamfer_tc::ctas_per_item(n, m);
+    if (per_item > 0 && 2 * per_item <= sms && chunks >= 3) {
+        // Tensor-core search: one CTA per SM, so a launch costs whole waves of the grid.  Slices of 1, 2, 3, 3, ...
+        // waves: the first copy-in is short, every later copy-in hides behind the previous slice's search, and no
+        // slice pays for a nearly empty final wave.  `chunks` is the maximum number of slices.
+        int k = 0, pos = 0, w = 1;
+        lo_of[0] = 0;
+        const int one_wave = sms / per_item;
+        while (pos < b) {
+            int take = (w * sms) / per_item;
+            if (k == chunks - 1 || b - pos - take < one_wave) take = b - pos;  // the last slice takes the remainder
+            lo_of[++k] = (pos += take);
+            if (w < 3) ++w;
+        }
+        chunks = k;
+    } else {
         const int edge = (chunks >= 3) ? ((b / 8 > 0) ? b / 8 : 1) : 0;
         const int inner = chunks - (edge ? 2 : 0), rest = b - 2 * edge;
         int pos = 0, k = 0;
@@ -100,7 +118,6 @@ extern "C" int geom_chamfer_fwd_host(geom_host_ctx *c, int b, int n, const float
     const size_t s_x1 = align_up(sizeof(float) * 3 * (size_t)b * n, 256), s_x2 = align_up(sizeof(float) * 3 * (size_t)b * m, 256);
     const size_t s_i1 = align_up(sizeof(int) * (size_t)b * n, 256), s_i2 = align_up(sizeof(int) * (size_t)b * m, 256);
     const size_t s_d1 = h_dist1 ? s_i1 : 0, s_d2 = h_dist2 ? s_i2 : 0;
-    const bool cuda_cores = (flags & (GEOM_FLAG_FP32 | GEOM_FLAG_ONEWAY)) != 0;
     const size_t ws_one = align_up(cuda_cores ? geom_chamfer_workspace_bytes(per, n, m) : geom_chamfer_tensor_workspace_bytes(per, n, m), 256);
     cudaError_t e = ensure_arena(c, s_x1 + s_x2 + s_i1 + s_i2 + s_d1 + s_d2 + ws_one * chunks);
     if (e != cudaSuccess) return geom::status_from_cuda(e);

@@ -95,8 +95,8 @@ GEOM_API int geom_chamfer_fwd(int b, int n, const float *xyz1, int m, const floa
                      void *workspace, size_t workspace_bytes, unsigned flags, geom_stream_t stream);
 
 /* Host-buffer form of geom_chamfer_fwd: every pointer is HOST memory (pinned memory gives full
- * copy/compute overlap; pageable memory works, staged by the driver).  The batch is cut into `chunks`
- * slices (<= 8; 0 = default 4): slice k+1 is copied to the device while slice k is searched and slice
+ * copy/compute overlap; pageable memory works, staged by the driver).  The batch is cut into at most `chunks`
+ * slices (<= 8; 0 = default 4; the library sizes them): slice k+1 is copied to the device while slice k is searched and slice
  * k-1's results are copied back, on three internal streams.  Synchronous: returns when all results
  * are in host memory.  h_dist1 / h_dist2 may be NULL.  A geom_host_ctx owns the streams, events and a
  * device arena reused across calls; create one per calling thread, on the device it should use.
