@@ -7,12 +7,15 @@
 //   which keeps the layer inside the 1e-5 parity budget that rules out a plain TF32 GEMM.
 //
 // One CTA computes a 128 x Npad output tile (Npad = N rounded up to 16, <= 256: one M=128 accumulator of
-// Npad TMEM columns), two CTAs per SM overlap each other's staging and MMA phases.  Per K-stage of 32:
-//   * all threads load the X tile (coalesced 128-byte row segments), split it into hi/lo TF32 and store
-//     both in the canonical no-swizzle K-major layout ([16-byte k-chunk][row][16 B]);
+// Npad TMEM columns), two CTAs per SM.  K is consumed in stages of 16 through TWO shared-memory buffers, so
+// the tensor core works on stage s while stage s+1 is being staged:
+//   * all threads load the X tile of the NEXT stage into registers (64-byte row segments) before they wait
+//     for anything, split it into hi/lo TF32 and store both in the canonical no-swizzle K-major layout
+//     ([16-byte k-chunk][row][16 B]) as soon as the MMAs that last read that buffer have completed;
 //   * the W tile comes pre-split and pre-arranged in that layout (wsplit_kernel, once per call: W is
-//     small) and is copied with cp.async;
-//   * one thread issues 4 k-substeps x 3 tcgen05.mma (kind::tf32, K = 8) and commits to an mbarrier.
+//     small); one thread fetches its eight 4 KB planes with TMA bulk copies (mbarrier complete_tx);
+//   * the same thread issues 2 k-substeps x 3 tcgen05.mma (kind::tf32, K = 8) and commits to the buffer's
+//     mbarrier.
 // Epilogue: tcgen05.ld -> shared-memory transpose -> coalesced row writes with the 0N-GCN routing
 // (columns < ksplit to the smoothing scratch T, the rest straight to Y with bias / ReLU).
 #include "common.cuh"
@@ -20,7 +23,7 @@
 namespace geom {
 namespace gcn_tc {
 
-constexpr int BK = 32;              // fp32 k-elements per stage
+constexpr int BK = 16;              // fp32 k-elements per stage
 constexpr int kChunks = BK / 4;     // 16-byte chunks per row per stage
 constexpr int kThreads = 256;
 constexpr int kMaxN = 256;
@@ -93,15 +96,32 @@ struct Args {
     int M, K, N, Npad, ksplit, ldt, relu, nstages;
 };
 
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    unsigned done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+    }
+}
+// TMA bulk copy global -> shared, completion counted in bytes on `bar` (expect_tx posted by the caller)
+__device__ __forceinline__ void tma_load(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 __global__ void __launch_bounds__(kThreads, 2) gemm_kernel(const Args g)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const int bplane = g.Npad * 16 + 16;  // bytes between k-chunk planes of the B tile
-    unsigned char *sAhi = smem;
-    unsigned char *sAlo = sAhi + kChunks * kAPlane;
-    unsigned char *sBhi = sAlo + kChunks * kAPlane;
-    unsigned char *sBlo = sBhi + kChunks * bplane;
-    __shared__ __align__(8) unsigned long long mma_bar;
+    const int abytes = 2 * kChunks * kAPlane, bbytes = 2 * kChunks * bplane;
+    // buffer i: [A hi planes | A lo planes | B hi planes | B lo planes]
+    auto buf_of = [&](int s) { return smem + (size_t)(s & 1) * (size_t)(abytes + bbytes); };
+    __shared__ __align__(8) unsigned long long mma_done[2], b_full[2];
     __shared__ unsigned tmem_slot;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -113,30 +133,44 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_kernel(const Args g)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(ncols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
+    auto load_b = [&](int s) {  // one thread: eight plane copies of stage s into buffer s & 1
+        unsigned char *sb = buf_of(s) + abytes;
+        const unsigned plane = (unsigned)g.Npad * 16u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&b_full[s & 1])), "r"(2u * kChunks * plane) : "memory");
+        const uint4 *ghi = g.Bhi + (size_t)s * kChunks * g.Npad;
+        const uint4 *glo = g.Blo + (size_t)s * kChunks * g.Npad;
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+            tma_load(sb + c * bplane, ghi + (size_t)c * g.Npad, plane, &b_full[s & 1]);
+            tma_load(sb + (kChunks + c) * bplane, glo + (size_t)c * g.Npad, plane, &b_full[s & 1]);
+        }
+    };
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&mma_bar)), "r"(1u));
-        asm volatile("fence.mbarrier_init.release.cluster;");
+        for (int i = 0; i < 2; ++i) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&mma_done[i])), "r"(1u));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&b_full[i])), "r"(1u));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        load_b(0);
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const unsigned tmem = tmem_slot;
     // D = f32 (1<<4), A = B = tf32 (2<<7, 2<<10), both K-major, N>>3 at bit 17, M>>4 at bit 24
     const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(g.Npad >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
     const bool xvec = (g.K % 4 == 0) && (((uintptr_t)g.X & 15u) == 0);
+    constexpr int kLoads = 128 * kChunks / kThreads;  // float4 per thread per stage
 
-    for (int s = 0; s < g.nstages; ++s) {
-        // ---- X tile: 128 rows x 8 chunks; thread -> (row = q / 8, chunk = q % 8): 128-byte row segments
+    // X tile: 128 rows x 4 chunks; thread -> (row = q / 4, chunk = q % 4): 64-byte row segments
+    auto load_x = [&](int s, float4 (&xa)[kLoads]) {
 #pragma unroll
-        for (int i = 0; i < 128 * kChunks / kThreads; ++i) {
+        for (int i = 0; i < kLoads; ++i) {
             const int q = tid + kThreads * i;
-            const int row = q >> 3, c = q & 7;
+            const int row = q >> 2, c = q & 3;
             const int r = m0 + row, k = s * BK + c * 4;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (r < g.M) {
                 const float *src = g.X + (size_t)r * g.K + k;
                 if (xvec && k + 3 < g.K) {
-                    v = *reinterpret_cast<const float4 *>(src);
+                    v = __ldg(reinterpret_cast<const float4 *>(src));
                 } else {
                     if (k + 0 < g.K) v.x = src[0];
                     if (k + 1 < g.K) v.y = src[1];
@@ -144,28 +178,37 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_kernel(const Args g)
                     if (k + 3 < g.K) v.w = src[3];
                 }
             }
+            xa[i] = v;
+        }
+    };
+    float4 xa[kLoads];
+    load_x(0, xa);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem = tmem_slot;
+
+    for (int s = 0; s < g.nstages; ++s) {
+        unsigned char *sAhi = buf_of(s), *sAlo = sAhi + kChunks * kAPlane;
+        unsigned char *sBhi = sAhi + abytes, *sBlo = sBhi + kChunks * bplane;
+        // buffer s & 1 was last read by the MMAs of stage s-2
+        if (s >= 2) mbar_wait(&mma_done[s & 1], (unsigned)(((s >> 1) - 1) & 1));
+#pragma unroll
+        for (int i = 0; i < kLoads; ++i) {
+            const int q = tid + kThreads * i;
+            const int row = q >> 2, c = q & 3;
             uint4 hi, lo;
-            split4(v, hi, lo);
+            split4(xa[i], hi, lo);
             *reinterpret_cast<uint4 *>(sAhi + c * kAPlane + row * 16) = hi;
             *reinterpret_cast<uint4 *>(sAlo + c * kAPlane + row * 16) = lo;
         }
-        // ---- W tile (pre-split, pre-arranged): plane by plane
-        {
-            const uint4 *ghi = g.Bhi + (size_t)s * kChunks * g.Npad;
-            const uint4 *glo = g.Blo + (size_t)s * kChunks * g.Npad;
-            for (int q = tid; q < kChunks * g.Npad; q += kThreads) {
-                const int c = q / g.Npad, n = q - c * g.Npad;
-                cp_async16(sBhi + c * bplane + n * 16, ghi + q);
-                cp_async16(sBlo + c * bplane + n * 16, glo + q);
-            }
-            cp_async_commit();
-            cp_async_wait_all();
-        }
+        if (s + 1 < g.nstages) load_x(s + 1, xa);  // in flight while this stage's MMAs are issued and run
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (tid == 0) {
+            mbar_wait(&b_full[s & 1], (unsigned)((s >> 1) & 1));
 #pragma unroll
             for (int sub = 0; sub < BK / 8; ++sub) {  // one K = 8 MMA covers chunks 2*sub, 2*sub+1
                 const u64 ah = make_desc(smem_u32(sAhi + 2 * sub * kAPlane), kAPlane, 128);
@@ -177,21 +220,20 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_kernel(const Args g)
                 mma_tf32(tmem, ah, bl, idesc, 1u);
                 mma_tf32(tmem, ah, bh, idesc, 1u);
             }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mma_bar)) : "memory");
-        }
-        // the staging buffers are reused by the next stage: wait for this stage's MMAs
-        {
-            unsigned done = 0;
-            const unsigned parity = (unsigned)(s & 1);
-            while (!done) {
-                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                             : "=r"(done)
-                             : "r"(smem_u32(&mma_bar)), "r"(parity)
-                             : "memory");
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mma_done[s & 1])) : "memory");
+            if (s + 1 < g.nstages) {
+                // the other buffer's W planes are read by the MMAs of stage s-1: refill it once they are done
+                if (s >= 1) mbar_wait(&mma_done[(s + 1) & 1], (unsigned)(((s - 1) >> 1) & 1));
+                load_b(s + 1);
             }
         }
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
+    // all MMAs complete (the last commit covers every earlier one)
+    {
+        const int last = g.nstages - 1;
+        mbar_wait(&mma_done[last & 1], (unsigned)((last >> 1) & 1));
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
     // ---- epilogue: warp w reads TMEM lanes 32*(w&3).. (rows) and the column chunks c0 = 32*(2*j + (w>>2))
     float *tile = reinterpret_cast<float *>(smem) + warp * (32 * 33);  // staging area is free now
@@ -266,7 +308,7 @@ cudaError_t launch(int M, int K, int N, const float *X, const float *W, const fl
     if (e != cudaSuccess) return e;
     g.X = X, g.Bhi = bhi, g.Blo = blo, g.bias = bias, g.Y = Y, g.T = T;
     g.M = M, g.K = K, g.N = N, g.ksplit = ksplit, g.ldt = ldt, g.relu = relu;
-    const size_t smem = 2 * (size_t)kChunks * kAPlane + 2 * (size_t)kChunks * (g.Npad * 16 + 16);
+    const size_t smem = 2 * (2 * (size_t)kChunks * kAPlane + 2 * (size_t)kChunks * (g.Npad * 16 + 16));  // two buffers
     const size_t epi = 8 * 32 * 33 * sizeof(float);
     const size_t dyn = smem > epi ? smem : epi;
     static bool attr_set = false;

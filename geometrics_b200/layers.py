@@ -160,7 +160,7 @@ class ZeroNGCNFunction(torch.autograd.Function):
         return dx, dw, db, None, None, None, None
 
 
-TENSOR_GEMM = False  # feature GEMM on the tensor cores (3xTF32 tcgen05) when the shape allows
+TENSOR_GEMM = True  # feature GEMM on the tensor cores (3xTF32 tcgen05) whenever the shape allows (out >= 16, <= 256)
 
 
 def zeron_gcn(x, weight, bias, adj, split: int, activation=None, tensor=None):
