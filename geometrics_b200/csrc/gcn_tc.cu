@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_kernel(const Args g)
             if (r < g.M) {
                 const float *src = g.X + (size_t)r * g.K + k;
                 if (xvec && k + 3 < g.K) {
-                    v = __ldg(reinterpret_cast<const float4 *>(src));
+                    v = *reinterpret_cast<const float4 *>(src);
                 } else {
                     if (k + 0 < g.K) v.x = src[0];
                     if (k + 1 < g.K) v.y = src[1];

@@ -8,6 +8,7 @@ columns) instead of two cuBLAS calls against the dense matrix.  CUDA only.
 from __future__ import annotations
 
 import math
+import weakref
 
 import torch
 import torch.nn.functional as F
@@ -43,7 +44,9 @@ def _build_csr(adj: torch.Tensor, transpose: bool):
 
 
 def csr_from_dense(adj: torch.Tensor) -> CsrAdjacency:
-    """CSR (+ transposed CSR) of a dense (V,V) fp32 CUDA adjacency; cached on (storage, version)."""
+    """CSR (+ transposed CSR) of a dense (V,V) fp32 CUDA adjacency; cached on (storage pointer, version) for as
+    long as the tensor object the entry was built from is alive (a dead owner means the allocator may have handed
+    the same address to a different matrix, so the entry is dropped and rebuilt)."""
     if adj.dim() != 2 or adj.shape[0] != adj.shape[1]:
         raise ValueError(f"adj must be a square (V,V) matrix, got {tuple(adj.shape)}")
     if not adj.is_cuda:
@@ -53,7 +56,10 @@ def csr_from_dense(adj: torch.Tensor) -> CsrAdjacency:
     key = (adj.data_ptr(), adj._version, adj.shape[0], adj.device.index, adj.is_contiguous())
     hit = _csr_cache.get(key)
     if hit is not None:
-        return hit
+        owner, cached = hit
+        if owner() is not None:  # the owner keeps the storage alive: same pointer + version == same contents
+            return cached
+        del _csr_cache[key]
     a = adj.detach().contiguous()
     with torch.cuda.device(a.device):
         c = CsrAdjacency()
@@ -62,7 +68,7 @@ def csr_from_dense(adj: torch.Tensor) -> CsrAdjacency:
         _, c.t_row_ptr, c.t_col_idx, c.t_val = _build_csr(a, True)
     if len(_csr_cache) >= _CSR_CACHE_MAX:
         _csr_cache.pop(next(iter(_csr_cache)))
-    _csr_cache[key] = c
+    _csr_cache[key] = (weakref.ref(adj), c)
     return c
 
 
