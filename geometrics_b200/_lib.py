@@ -46,6 +46,8 @@ SYMBOLS = {
     "geom_face_areas": (_i, [_i, _i, _vp, _i, _vp, _vp, _i, _vp]),
     "geom_sample_fwd": (_i, [_i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "geom_sample_bwd": (_i, [_i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "geom_pool_fwd": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "geom_pool_bwd": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "geom_csr_count": (_i, [_i, _vp, _i, _vp, _vp, _vp]),
     "geom_csr_fill": (_i, [_i, _vp, _i, _vp, _vp, _vp, _vp]),
     "geom_csr_spmm": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -91,7 +93,7 @@ def lib() -> C.CDLL:
     return _lib
 
 
-GEOM_PROF_KERNELS = 18
+GEOM_PROF_KERNELS = 20
 
 
 def prof_begin() -> None:

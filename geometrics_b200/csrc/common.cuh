@@ -116,7 +116,7 @@ namespace prof {
 enum Kernel {
     kChamferTwoWay = 0, kChamferRefine, kChamferOneWay, kTri, kChamferLoss, kChamferLossBwd,
     kSampleFwd, kSampleBwd, kSampleArea, kGcnGemm, kGcnSpmm, kGcnBwd, kTriClosest, kTriClosestBwd,
-    kMisc, kMisc2, kChamferTcScan, kChamferTcPack, kKernelCount
+    kMisc, kMisc2, kChamferTcScan, kChamferTcPack, kPoolFwd, kPoolBwd, kKernelCount
 };
 static_assert(kKernelCount == GEOM_PROF_KERNELS, "geom_b200.h GEOM_PROF_KERNELS out of sync");
 struct Scope {

@@ -280,12 +280,33 @@ spmm_kernel(int rows, int V, int N, int ksplit, int ldt, const int *__restrict__
     const int bi = row / V, i = row - bi * V;
     const int p0 = row_ptr[i], p1 = row_ptr[i + 1];
     const float *Tb = T + (size_t)bi * V * ldt;
-    for (int c = lane; c < ksplit; c += 32) {
-        float acc = 0.f;
-        for (int p = p0; p < p1; ++p) acc = fmaf(val[p], Tb[(size_t)col_idx[p] * ldt + c], acc);
-        float o = bias ? acc + bias[c] : acc;
-        if (relu) o = fmaxf(o, 0.f);
-        Y[(size_t)row * N + c] = o;
+    // Four columns per lane: the T rows are ldt = round4(ksplit) floats, 16-byte aligned, so a neighbour's row is
+    // read with 128-bit loads (22 lanes cover k = 85).  Each column keeps the scalar kernel's fmaf chain over the
+    // neighbours in CSR order, so the result is bit-identical to a one-column-per-lane sweep.  Columns
+    // ksplit..ldt-1 of T are never written by the GEMM: they are accumulated but not stored.
+    const bool vec_store = (N & 3) == 0 && (((uintptr_t)Y & 15u) == 0);
+    for (int q = lane; q < (ldt >> 2); q += 32) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int p = p0; p < p1; ++p) {
+            const float w = val[p];
+            const float4 t = *reinterpret_cast<const float4 *>(Tb + (size_t)col_idx[p] * ldt + 4 * q);
+            acc.x = fmaf(w, t.x, acc.x), acc.y = fmaf(w, t.y, acc.y), acc.z = fmaf(w, t.z, acc.z), acc.w = fmaf(w, t.w, acc.w);
+        }
+        const int c = 4 * q;
+        float o[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (bias && c + j < ksplit) o[j] += bias[c + j];
+            if (relu) o[j] = fmaxf(o[j], 0.f);
+        }
+        float *dst = Y + (size_t)row * N + c;
+        if (vec_store && c + 3 < ksplit) {
+            *reinterpret_cast<float4 *>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (c + j < ksplit) dst[j] = o[j];
+        }
     }
 }
 

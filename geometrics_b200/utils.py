@@ -358,3 +358,127 @@ def batch_get_lap_info(positions, adj_info):
         scaler = _degree_cache[key] = (1. / (torch.sum(orig, dim=1) - 1)).view(-1, 1)
     neighbor_sum = (csr_matmul(orig, positions) - positions) * scaler
     return positions - neighbor_sum
+
+
+# ------------------------------------------------------------------------------------------------
+# vertex feature pooling (utils.py:283-389)
+# ------------------------------------------------------------------------------------------------
+def batch_camera_info(param: torch.Tensor):
+    """utils.py:283-312: camera matrix (B,3,3) and position (B,3) from (azimuth deg, elevation deg, distance)
+    rows.  Same expressions in the same order (incl. the ``% 360.`` applied to radians), device-agnostic."""
+    import math
+
+    theta = (math.pi * param[:, 0] / 180.) % 360.
+    phi = (math.pi * param[:, 1] / 180.) % 360.
+    cam_y = param[:, 2] * torch.sin(phi)
+    temp = param[:, 2] * torch.cos(phi)
+    cam_x = temp * torch.cos(theta)
+    cam_z = temp * torch.sin(theta)
+    cam_pos = torch.cat((cam_x.unsqueeze(1), cam_y.unsqueeze(1), cam_z.unsqueeze(1)), dim=1)
+    axis_z = cam_pos.clone()
+    axis_y = torch.tensor([0., 1., 0.], dtype=param.dtype, device=param.device).unsqueeze(0).expand(axis_z.shape[0], 3)
+    axis_x = torch.linalg.cross(axis_y, axis_z, dim=1)
+    axis_y = torch.linalg.cross(axis_z, axis_x, dim=1)
+    axis_x = axis_x / torch.sqrt(torch.sum(axis_x ** 2, dim=1)).unsqueeze(-1)
+    axis_y = axis_y / torch.sqrt(torch.sum(axis_y ** 2, dim=1)).unsqueeze(-1)
+    axis_z = axis_z / torch.sqrt(torch.sum(axis_z ** 2, dim=1)).unsqueeze(-1)
+    cam_mat = torch.cat((axis_x.unsqueeze(1), axis_y.unsqueeze(1), axis_z.unsqueeze(1)), dim=1)
+    return cam_mat, cam_pos
+
+
+def project_vertices(verts_pos: torch.Tensor, img_info: torch.Tensor):
+    """utils.py:319-330: image-plane coordinates of the vertices as fractions of the image size -> (xs, ys), (B,V)."""
+    cam_mat, cam_pos = batch_camera_info(img_info)
+    pt = torch.matmul((verts_pos * .57) - cam_pos.unsqueeze(1), cam_mat.permute(0, 2, 1))
+    x, y, z = pt[:, :, 0], pt[:, :, 1], pt[:, :, 2]
+    f = 248
+    h = (-y) / (-z) * f + 224 / 2.0
+    w = x / (-z) * f + 224 / 2.0
+    return h / 223., w / 223.
+
+
+class PoolFunction(torch.autograd.Function):
+    """(xs, ys, *maps) -> (B, V, sum C): geom_pool_fwd / geom_pool_bwd."""
+
+    @staticmethod
+    def forward(ctx, xs, ys, out_buf, col0, *maps):
+        import ctypes as C
+
+        L = _lib.lib()
+        xs, ys = xs.detach().contiguous(), ys.detach().contiguous()
+        maps = tuple(m.detach().contiguous() for m in maps)
+        b, v = xs.shape
+        dev = xs.device
+        chans = [int(m.shape[1]) for m in maps]
+        dims = [int(m.shape[-1]) for m in maps]
+        total = sum(chans)
+        with torch.cuda.device(dev):
+            out = out_buf if out_buf is not None else torch.empty((b, v, total), dtype=torch.float32, device=dev)
+            ptrs = (C.c_void_p * len(maps))(*[m.data_ptr() for m in maps])
+            ch = (C.c_int * len(maps))(*chans)
+            dm = (C.c_int * len(maps))(*dims)
+            _lib.check(L.geom_pool_fwd(b, v, len(maps), ptrs, ch, dm, xs.data_ptr(), ys.data_ptr(), out.data_ptr(),
+                                       out.shape[2], int(col0), _lib.current_stream_ptr(dev)), "geom_pool_fwd")
+        ctx.save_for_backward(xs, ys, *maps)
+        ctx.meta = (chans, dims, int(col0), out.shape[2])
+        if out_buf is not None:
+            ctx.mark_dirty(out_buf)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        import ctypes as C
+
+        L = _lib.lib()
+        xs, ys, *maps = ctx.saved_tensors
+        chans, dims, col0, ld = ctx.meta
+        b, v = xs.shape
+        dev = xs.device
+        dout = dout.contiguous()
+        want_maps = [ctx.needs_input_grad[4 + k] for k in range(len(maps))]
+        with torch.cuda.device(dev):
+            gmaps = [torch.zeros_like(m) if w else None for m, w in zip(maps, want_maps)]
+            gxs = torch.empty_like(xs) if ctx.needs_input_grad[0] else None
+            gys = torch.empty_like(ys) if ctx.needs_input_grad[1] else None
+            ptrs = (C.c_void_p * len(maps))(*[m.data_ptr() for m in maps])
+            gptrs = (C.c_void_p * len(maps))(*[gm.data_ptr() if gm is not None else None for gm in gmaps])
+            ch = (C.c_int * len(maps))(*chans)
+            dm = (C.c_int * len(maps))(*dims)
+            _lib.check(L.geom_pool_bwd(b, v, len(maps), ptrs, gptrs, ch, dm, xs.data_ptr(), ys.data_ptr(), dout.data_ptr(),
+                                       ld, col0, gxs.data_ptr() if gxs is not None else None,
+                                       gys.data_ptr() if gys is not None else None, _lib.current_stream_ptr(dev)), "geom_pool_bwd")
+        return (gxs, gys, None, None, *gmaps)
+
+
+def pool_features(blocks, xs: torch.Tensor, ys: torch.Tensor, out: torch.Tensor = None, col0: int = 0) -> torch.Tensor:
+    """Bilinear gather of every feature map in ``blocks`` (each (B,C,dim,dim)) at the projected coordinates.
+    ``out`` (B,V,ld) / ``col0``: gather straight into columns [col0, col0 + sum C) of an existing buffer (e.g. the
+    deformation block's input, next to the vertex positions) instead of allocating the result."""
+    _lib.require_cuda_f32("xs", xs)
+    _lib.require_cuda_f32("ys", ys)
+    if xs.shape != ys.shape or xs.dim() != 2:
+        raise ValueError(f"xs / ys must be (B,V), got {tuple(xs.shape)} and {tuple(ys.shape)}")
+    blocks = list(blocks)
+    if len(blocks) > 8:
+        raise ValueError("at most 8 feature maps per call")
+    for i, blk in enumerate(blocks):
+        _lib.require_cuda_f32(f"blocks[{i}]", blk)
+        if blk.dim() != 4 or blk.shape[0] != xs.shape[0] or blk.shape[2] != blk.shape[3]:
+            raise ValueError(f"blocks[{i}] must be (B,C,dim,dim) with B={xs.shape[0]}, got {tuple(blk.shape)}")
+    if out is not None:
+        _lib.require_cuda_f32("out", out)
+        total = sum(int(blk.shape[1]) for blk in blocks)
+        if out.dim() != 3 or tuple(out.shape[:2]) != tuple(xs.shape) or not out.is_contiguous() or col0 < 0 \
+                or col0 + total > out.shape[2]:
+            raise ValueError(f"out must be a contiguous (B,V,ld) buffer with ld >= col0 + {total}, got {tuple(out.shape)}")
+    return PoolFunction.apply(xs, ys, out, int(col0), *blocks)
+
+
+def batched_pooling(blocks, verts_pos: torch.Tensor, img_info: torch.Tensor) -> torch.Tensor:
+    """utils.py:316-389, same signature: per-vertex features (B,V,sum C) gathered from the CNN feature maps at the
+    vertices' image positions.  The projection is the reference's handful of (B,V) elementwise ops; the gather
+    (4 index_selects, permutes, weights and the cat per map in the reference) is one kernel, differentiable with
+    respect to the maps and the vertex positions."""
+    _lib.require_cuda_f32("verts_pos", verts_pos, 3)
+    xs, ys = project_vertices(verts_pos, img_info)
+    return pool_features(blocks, xs, ys)

@@ -70,7 +70,7 @@ GEOM_API int geom_device_info(int *sm_count, int *cc_major, int *cc_minor);
  * the API is bracketed by CUDA events on its launch stream; geom_prof_end() synchronises on them and
  * returns, per kernel id, the summed device milliseconds and the launch count (arrays of
  * GEOM_PROF_KERNELS entries, either may be NULL).  Used by bench.py for the roofline figures. */
-#define GEOM_PROF_KERNELS 18
+#define GEOM_PROF_KERNELS 20
 GEOM_API int geom_prof_begin(void);
 GEOM_API int geom_prof_end(float *ms_per_kernel, int *launches_per_kernel);
 GEOM_API const char *geom_prof_kernel_name(int id);
@@ -187,6 +187,27 @@ GEOM_API int geom_sample_fwd(int b, int V, const float *verts, int F, const int6
 GEOM_API int geom_sample_bwd(int b, int V, int F, const int64_t *faces, int num, const int64_t *choices,
                     const float *r1, const float *r2, const float *grad_points, float *grad_verts,
                     geom_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Vertex feature pooling.
+ * Replaces the gather part of batched_pooling (utils.py:331-389): for every vertex and every feature map
+ * (NCHW fp32, square dim x dim), the reference's bilinear combination of the 4 texels around
+ * (clamp(xs*dim, 0, dim-1), clamp(ys*dim, 0, dim-1)), bit-identical to the torch expression for identical
+ * projected coordinates xs, ys (B,V) -- including its zero result when a clamped coordinate is integral
+ * (floor == ceil makes both weights 0, utils.py:341-346).  The projection itself (batch_camera_info and
+ * utils.py:319-330, a few elementwise ops on (B,V) tensors) stays with the caller.
+ * geom_pool_fwd: out[b, v, col0 + c] for c over the concatenated channels of the n_maps (<= 8) maps; `out` is a
+ *   (B, V, ld) buffer, so the caller can gather straight into the block input next to the vertex positions
+ *   (models.py:239 concatenates them).  maps / channels / dims are HOST arrays of n_maps entries.
+ * geom_pool_bwd: grad_maps[k] += scatter-add of the weighted grad_out (caller zero-initialises; entries may be
+ *   NULL), grad_xs / grad_ys (B,V) = gradient through the bilinear weights (either may be NULL); floor, ceil and
+ *   clamp carry torch's gradients (0, 0, pass-through inside [0, dim-1]).
+ * ------------------------------------------------------------------------------------------- */
+GEOM_API int geom_pool_fwd(int b, int V, int n_maps, const float *const *maps, const int *channels, const int *dims,
+                  const float *xs, const float *ys, float *out, int ld, int col0, geom_stream_t stream);
+GEOM_API int geom_pool_bwd(int b, int V, int n_maps, const float *const *maps, float *const *grad_maps,
+                  const int *channels, const int *dims, const float *xs, const float *ys, const float *grad_out,
+                  int ld, int col0, float *grad_xs, float *grad_ys, geom_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * 0N-GCN layer.

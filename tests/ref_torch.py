@@ -108,3 +108,60 @@ def zeron_gcn(x, weight, bias, adj, split):
     k = support.shape[-1] // split
     out = torch.cat((torch.matmul(adj, support[..., :k]), support[..., k:]), dim=-1)
     return out + bias if bias is not None else out
+
+
+def batch_camera_info(param):
+    """utils.py:283-312 restated device-agnostically (same expressions, same order)."""
+    import math
+
+    theta = (math.pi * param[:, 0] / 180.) % 360.
+    phi = (math.pi * param[:, 1] / 180.) % 360.
+    cam_y = param[:, 2] * torch.sin(phi)
+    temp = param[:, 2] * torch.cos(phi)
+    cam_x = temp * torch.cos(theta)
+    cam_z = temp * torch.sin(theta)
+    cam_pos = torch.cat((cam_x.unsqueeze(1), cam_y.unsqueeze(1), cam_z.unsqueeze(1)), dim=1)
+    axis_z = cam_pos.clone()
+    axis_y = torch.tensor([0., 1., 0.], device=param.device).unsqueeze(0).expand(axis_z.shape[0], 3)
+    axis_x = torch.linalg.cross(axis_y, axis_z, dim=1)
+    axis_y = torch.linalg.cross(axis_z, axis_x, dim=1)
+    axis_x = axis_x / torch.sqrt(torch.sum(axis_x ** 2, dim=1)).unsqueeze(-1)
+    axis_y = axis_y / torch.sqrt(torch.sum(axis_y ** 2, dim=1)).unsqueeze(-1)
+    axis_z = axis_z / torch.sqrt(torch.sum(axis_z ** 2, dim=1)).unsqueeze(-1)
+    return torch.cat((axis_x.unsqueeze(1), axis_y.unsqueeze(1), axis_z.unsqueeze(1)), dim=1), cam_pos
+
+
+def project_vertices(verts_pos, img_info):
+    """utils.py:319-330."""
+    cam_mat, cam_pos = batch_camera_info(img_info)
+    pt = torch.matmul((verts_pos * .57) - cam_pos.unsqueeze(1), cam_mat.permute(0, 2, 1))
+    x, y, z = pt[:, :, 0], pt[:, :, 1], pt[:, :, 2]
+    h = (-y) / (-z) * 248 + 224 / 2.0
+    w = x / (-z) * 248 + 224 / 2.0
+    return h / 223., w / 223.
+
+
+def pool_features(blocks, xs, ys):
+    """utils.py:331-389: the bilinear gather, with the reference's association order
+    (A*C)*G + (H*D)*A + (G*E)*B + (B*F)*H and its floor == ceil -> zero-weight quirk."""
+    b, v = xs.shape
+    outs = []
+    for blk in blocks:
+        dim = blk.shape[-1]
+        cx, cy = torch.clamp(xs * dim, 0, dim - 1), torch.clamp(ys * dim, 0, dim - 1)
+        x1, y1, x2, y2 = torch.floor(cx), torch.floor(cy), torch.ceil(cx), torch.ceil(cy)
+        wa, wb, wg, wh = x2 - cx, cx - x1, y2 - cy, cy - y1
+        flat = blk.reshape(b, blk.shape[1], dim * dim)
+
+        def take(xi, yi):
+            idx = (xi.long() * dim + yi.long()).unsqueeze(1).expand(b, blk.shape[1], v)
+            return torch.gather(flat, 2, idx)
+
+        f = wa.unsqueeze(1) * take(x1, y1) * wg.unsqueeze(1) + wh.unsqueeze(1) * take(x1, y2) * wa.unsqueeze(1) \
+            + wg.unsqueeze(1) * take(x2, y1) * wb.unsqueeze(1) + wb.unsqueeze(1) * take(x2, y2) * wh.unsqueeze(1)
+        outs.append(f.permute(0, 2, 1))
+    return torch.cat(outs, dim=2)
+
+
+def batched_pooling(blocks, verts_pos, img_info):
+    return pool_features(blocks, *project_vertices(verts_pos, img_info))

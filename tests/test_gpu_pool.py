@@ -1,0 +1,82 @@
+"""GPU: the fused vertex-pooling kernel (geom_pool_fwd / geom_pool_bwd) against the torch
+restatement of utils.py:316-389 (tests/ref_torch.py, itself pinned to the reference's own output on CPU by
+tests/test_pool_cpu.py) and against that golden output directly."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import ref_torch as R
+from golden import make_golden_pool as G
+from helpers import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def test_forward_bit_exact_vs_reference_golden(cuda):
+    """Same projected coordinates (computed on the CPU like the golden run) -> the reference's bits."""
+    import geometrics_b200.utils as U
+
+    gold = np.load(os.path.join(GOLDEN, "pool_ref.npz"))
+    verts, img_info, blocks = G.inputs()
+    xs, ys = R.project_vertices(verts, img_info)
+    got = U.pool_features([b.to(cuda) for b in blocks], xs.to(cuda), ys.to(cuda))
+    assert np.array_equal(got.cpu().numpy(), gold["feats"])
+    assert int((got.abs().sum(-1) == 0).sum()) >= 1  # clamped vertices: the floor == ceil zero-weight quirk
+
+
+@pytest.mark.parametrize("shape", [(2, 96, ((5, 56), (7, 28), (33, 14), (40, 7))), (3, 482, ((64, 56), (128, 28), (256, 14), (512, 7))),
+                                   (1, 31, ((3, 9),)), (2, 33, ((1, 5), (70, 3)))])
+def test_forward_and_backward_vs_torch(cuda, shape):
+    import geometrics_b200.utils as U
+
+    b, v, maps = shape
+    g = torch.Generator().manual_seed(3)
+    verts = (torch.rand(b, v, 3, generator=g) - 0.5)
+    verts[:, :4] *= 3.0
+    img_info = torch.stack((torch.rand(b, generator=g) * 360., 25. + 5. * torch.rand(b, generator=g),
+                            0.6 + 0.4 * torch.rand(b, generator=g)), dim=1).to(cuda)
+    blocks = [torch.randn(b, c, d, d, generator=g).to(cuda) for c, d in maps]
+    up = torch.randn(b, v, sum(c for c, _ in maps), generator=g).to(cuda)
+    res = []
+    for fn in (U.batched_pooling, R.batched_pooling):
+        p = verts.to(cuda).requires_grad_(True)
+        bl = [x.clone().requires_grad_(True) for x in blocks]
+        f = fn(bl, p, img_info)
+        (f * up).sum().backward()
+        res.append((f.detach(), p.grad, [x.grad for x in bl]))
+    (f0, dp0, db0), (f1, dp1, db1) = res
+    assert torch.equal(f0, f1), f"forward differs: {float((f0 - f1).abs().max())}"
+    scale = float(dp1.abs().max())
+    assert float((dp0 - dp1).abs().max()) <= 2e-4 * scale, (float((dp0 - dp1).abs().max()), scale)
+    for a, r in zip(db0, db1):
+        assert float((a - r).abs().max()) <= 1e-5 * max(1.0, float(r.abs().max()))
+
+
+def test_gather_into_block_input_buffer(cuda):
+    """out / col0: features written next to the vertex positions (what models.py:239 concatenates)."""
+    import geometrics_b200.utils as U
+
+    verts, img_info, blocks = G.inputs()
+    verts, img_info, blocks = verts.to(cuda), img_info.to(cuda), [b.to(cuda) for b in blocks]
+    xs, ys = U.project_vertices(verts, img_info)
+    want = U.pool_features(blocks, xs, ys)
+    buf = torch.full((2, 96, 3 + want.shape[2] + 2), -7.0, device=cuda)
+    buf[:, :, :3] = verts
+    out = U.pool_features(blocks, xs, ys, out=buf, col0=3)
+    assert out.data_ptr() == buf.data_ptr()
+    assert torch.equal(buf[:, :, 3:3 + want.shape[2]], want) and torch.equal(buf[:, :, :3], verts)
+    assert bool((buf[:, :, 3 + want.shape[2]:] == -7.0).all())
+
+
+def test_argument_validation(cuda):
+    import geometrics_b200.utils as U
+
+    xs = torch.rand(2, 10, device=cuda)
+    with pytest.raises(RuntimeError):
+        U.pool_features([torch.rand(2, 3, 4, 4)], xs, xs)            # CPU map
+    with pytest.raises(ValueError):
+        U.pool_features([torch.rand(2, 3, 4, 5, device=cuda)], xs, xs)  # not square
+    with pytest.raises(ValueError):
+        U.pool_features([torch.rand(3, 3, 4, 4, device=cuda)], xs, xs)  # batch mismatch

@@ -125,6 +125,32 @@ def main():
         return R.batch_sample_given(verts, fi, ch, torch.rand(32 * num, 1, device=dev), torch.rand(32 * num, 1, device=dev))
     emit("batch_sample end to end 32x10000 (areas+multinomial+gather)", ms, timeit(ref_full, reps=5), None, 32 * num, "samples", prof(f))
 
+    # ---------------- vertex feature pooling: B=16, V=482, VGG-sized maps (64/128/256/512 ch at 56/28/14/7)
+    vsp, _ = synth.uv_sphere(32, 15)
+    pverts = synth.mesh_batch(vsp, 16).to(dev)
+    gen = torch.Generator(device=dev).manual_seed(2)
+    info = torch.stack((torch.rand(16, device=dev, generator=gen) * 360., 25. + 5. * torch.rand(16, device=dev, generator=gen),
+                        0.6 + 0.4 * torch.rand(16, device=dev, generator=gen)), dim=1)
+    maps = [torch.randn(16, c, d, d, device=dev, generator=gen) for c, d in ((64, 56), (128, 28), (256, 14), (512, 7))]
+    f = lambda i: U.batched_pooling(maps, pverts, info)
+    ms = timeit(f, reps=50)
+    rms = timeit(lambda i: R.batched_pooling(maps, pverts, info), reps=20)
+    alg = 16 * 482 * 960 * 4 * 5 + 16 * 482 * 12  # 4 texel reads + 1 write per feature, positions
+    emit("batched_pooling fwd B=16 V=482 C=960 (projection + gather)", ms, rms, alg, 16 * 482 * 960, "features", prof(f))
+    mg = [m.clone().requires_grad_(True) for m in maps]
+    pg = pverts.clone().requires_grad_(True)
+
+    def pool_step(fn):
+        def run(i):
+            pg.grad = None
+            for m in mg:
+                m.grad = None
+            fn(mg, pg, info).sum().backward()
+        return run
+    ms = timeit(pool_step(U.batched_pooling), reps=30)
+    rms = timeit(pool_step(R.batched_pooling), reps=10)
+    emit("batched_pooling fwd+bwd B=16 V=482 C=960", ms, rms, None, 16 * 482 * 960, "features", prof(pool_step(U.batched_pooling)))
+
     # ---------------- losses at the training size (B=16, 3000 samples, 482-vertex mesh)
     vs, fs = synth.uv_sphere(32, 15)
     pv = synth.mesh_batch(vs, 16).to(dev).requires_grad_(True)
