@@ -34,6 +34,7 @@ SYMBOLS = {
     "geom_chamfer_fwd": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _u, _vp]),
     "geom_host_ctx_create": (_i, [C.POINTER(_vp)]),
     "geom_host_ctx_destroy": (_i, [_vp]),
+    "geom_chamfer_host_plan": (_i, [_i, _i, _i, _i, _u, _i, C.POINTER(_i)]),
     "geom_chamfer_fwd_host": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _u]),
     "geom_chamfer_loss_workspace_bytes": (_sz, [_i, _i, _i]),
     "geom_chamfer_loss_fwd": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

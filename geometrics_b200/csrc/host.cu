@@ -71,22 +71,15 @@ extern "C" int geom_host_ctx_destroy(geom_host_ctx *c)
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-extern "C" int geom_chamfer_fwd_host(geom_host_ctx *c, int b, int n, const float *h_xyz1, int m,
-                                     const float *h_xyz2, float *h_dist1, int *h_idx1, float *h_dist2,
-                                     int *h_idx2, int chunks, unsigned flags)
+// Slice plan of geom_chamfer_fwd_host: lo_of[k]..lo_of[k+1] is slice k; returns the number of slices (<= 8).
+extern "C" int geom_chamfer_host_plan(int b, int n, int m, int chunks, unsigned flags, int sm_count, int *lo_of)
 {
-    if (!c || b < 0 || n < 0 || m < 0) return GEOM_ERR_INVALID_ARG;
-    if (b == 0 || (n == 0 && m == 0)) return GEOM_OK;
-    if ((n > 0 && (!h_xyz1 || !h_idx1)) || (m > 0 && (!h_xyz2 || !h_idx2))) return GEOM_ERR_INVALID_ARG;
+    if (b < 1 || n < 0 || m < 0 || !lo_of) return 0;
     if (chunks < 1) chunks = 4;
     if (chunks > geom_host_ctx::kMaxChunks) chunks = geom_host_ctx::kMaxChunks;
     if (chunks > b) chunks = b;
-    // Slice boundaries: small first and last slices (only the first copy-in and the last copy-out are
-    // exposed), the rest split evenly.  lo[k]..lo[k+1] is slice k.
-    int lo_of[geom_host_ctx::kMaxChunks + 1];
     const bool cuda_cores = (flags & (GEOM_FLAG_FP32 | GEOM_FLAG_ONEWAY)) != 0;
-    int sms = 0;
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device) != cudaSuccess) sms = 0;
+    const int sms = sm_count;
     const int per_item = cuda_cores ? 0 : geom::chamfer_tc::ctas_per_item(n, m);
     if (per_item > 0 && 2 * per_item <= sms && chunks >= 3) {
         // Tensor-core search: one CTA per SM, so a launch costs whole waves of the grid.  Slices of 1, 2, 3, 3, ...
@@ -101,16 +94,33 @@ extern "C" int geom_chamfer_fwd_host(geom_host_ctx *c, int b, int n, const float
             lo_of[++k] = (pos += take);
             if (w < 3) ++w;
         }
-        chunks = k;
-    } else {
-        const int edge = (chunks >= 3) ? ((b / 8 > 0) ? b / 8 : 1) : 0;
-        const int inner = chunks - (edge ? 2 : 0), rest = b - 2 * edge;
-        int pos = 0, k = 0;
-        lo_of[k++] = 0;
-        if (edge) lo_of[k++] = (pos += edge);
-        for (int i = 0; i < inner; ++i) lo_of[k++] = (pos += rest / inner + (i < rest % inner ? 1 : 0));
-        if (edge) lo_of[k++] = (pos += edge);
+        return k;
     }
+    // CUDA-core search (ticket-scheduled, no wave quantisation): small first and last slices (only the first copy-in
+    // and the last copy-out are exposed), the rest split evenly.
+    const int edge = (chunks >= 3) ? ((b / 8 > 0) ? b / 8 : 1) : 0;
+    const int inner = chunks - (edge ? 2 : 0), rest = b - 2 * edge;
+    int pos = 0, k = 0;
+    lo_of[k++] = 0;
+    if (edge) lo_of[k++] = (pos += edge);
+    for (int i = 0; i < inner; ++i) lo_of[k++] = (pos += rest / inner + (i < rest % inner ? 1 : 0));
+    if (edge) lo_of[k++] = (pos += edge);
+    return k - 1;
+}
+
+extern "C" int geom_chamfer_fwd_host(geom_host_ctx *c, int b, int n, const float *h_xyz1, int m,
+                                     const float *h_xyz2, float *h_dist1, int *h_idx1, float *h_dist2,
+                                     int *h_idx2, int chunks, unsigned flags)
+{
+    if (!c || b < 0 || n < 0 || m < 0) return GEOM_ERR_INVALID_ARG;
+    if (b == 0 || (n == 0 && m == 0)) return GEOM_OK;
+    if ((n > 0 && (!h_xyz1 || !h_idx1)) || (m > 0 && (!h_xyz2 || !h_idx2))) return GEOM_ERR_INVALID_ARG;
+    int lo_of[geom_host_ctx::kMaxChunks + 1];
+    const bool cuda_cores = (flags & (GEOM_FLAG_FP32 | GEOM_FLAG_ONEWAY)) != 0;
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device) != cudaSuccess) sms = 0;
+    chunks = geom_chamfer_host_plan(b, n, m, chunks, flags, sms, lo_of);
+    if (chunks < 1) return GEOM_ERR_INVALID_ARG;
     int per = 0;
     for (int k = 0; k < chunks; ++k) per = (lo_of[k + 1] - lo_of[k] > per) ? lo_of[k + 1] - lo_of[k] : per;
 

@@ -15,7 +15,8 @@
 // x1 == x2, hence A == B == 0 and a ZERO feature (utils.py:341-346).  Every product / sum is rounded separately
 // (no FMA contraction), in the reference's association order.
 //
-// Layout: maps are NCHW fp32 (B, C, dim, dim); a CTA owns 32 consecutive vertices of one mesh; each warp takes
+// Layout: maps are NCHW fp32 (B, C, dim, dim); a CTA owns 32 consecutive vertices of one mesh and 128 channels of
+// one map (grid.z walks the (map, channel chunk) pairs); each warp takes
 // channels round-robin with lanes = vertices (the 4 corner reads of neighbouring vertices fall into the same
 // few rows of one 12 KB channel plane: L1/L2 hits), results go through a 32x33 shared-memory tile so that the
 // output rows are written as 128-byte segments.
@@ -30,13 +31,19 @@ namespace pool {
 constexpr int kMaxMaps = 8;
 constexpr int kVertsPerCta = 32;
 constexpr int kWarps = 8;
+constexpr int kChunk = 128;     // channels per CTA: blockIdx.z walks (map, channel chunk) pairs, so that the real
+constexpr int kMaxChunks = 64;  // shapes (16 meshes x 482 vertices x 960 channels) give ~2000 CTAs instead of 256
 
 struct Maps {
     const float *ptr[kMaxMaps];  // forward: feature maps; backward: unused
     float *grad[kMaxMaps];       // backward: gradient of the maps (accumulated into)
     int channels[kMaxMaps];
     int dim[kMaxMaps];
+    int col[kMaxMaps];                 // first output column of the map
     int n;
+    int n_chunks;
+    unsigned char chunk_map[kMaxChunks];   // chunk -> map
+    unsigned short chunk_c0[kMaxChunks];   // chunk -> first channel / kChunk
 };
 
 struct Corner {  // per (vertex, map): flat indices of the 4 corners inside one channel plane and the weights
@@ -63,22 +70,23 @@ __global__ void __launch_bounds__(kWarps * 32)
 fwd_kernel(int V, const Maps m, const float *__restrict__ xs, const float *__restrict__ ys,
            float *__restrict__ out, int ld, int col0)
 {
-    __shared__ Corner corners[kMaxMaps][kVertsPerCta];
+    __shared__ Corner corners[kVertsPerCta];
     __shared__ float tile[kVertsPerCta][33];
     const int b = blockIdx.y, v0 = blockIdx.x * kVertsPerCta;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int q = threadIdx.x; q < m.n * kVertsPerCta; q += kWarps * 32) {
-        const int k = q / kVertsPerCta, j = q - k * kVertsPerCta;
-        const int v = min(v0 + j, V - 1);
-        corners[k][j] = make_corner(xs[(size_t)b * V + v], ys[(size_t)b * V + v], m.dim[k], nullptr, nullptr);
+    const int k = m.chunk_map[blockIdx.z];
+    const int c_lo = (int)m.chunk_c0[blockIdx.z] * kChunk;
+    if (threadIdx.x < kVertsPerCta) {
+        const int v = min(v0 + (int)threadIdx.x, V - 1);
+        corners[threadIdx.x] = make_corner(xs[(size_t)b * V + v], ys[(size_t)b * V + v], m.dim[k], nullptr, nullptr);
     }
     __syncthreads();
-    int col = col0;
-    for (int k = 0; k < m.n; ++k) {
-        const int C = m.channels[k], plane = m.dim[k] * m.dim[k];
+    {
+        const int C = m.channels[k], plane = m.dim[k] * m.dim[k], col = m.col[k] + col0;
+        const int c_hi = min(C, c_lo + kChunk);
         const float *base = m.ptr[k] + (size_t)b * C * plane;
-        const Corner c = corners[k][lane];
-        for (int cb = 0; cb < C; cb += 32) {  // 32 channels per round: 4 per warp, then one coalesced flush
+        const Corner c = corners[lane];
+        for (int cb = c_lo; cb < c_hi; cb += 32) {  // 32 channels per round: 4 per warp, then one coalesced flush
 #pragma unroll
             for (int i = 0; i < 32 / kWarps; ++i) {
                 const int ch = cb + warp + kWarps * i;
@@ -102,7 +110,6 @@ fwd_kernel(int V, const Maps m, const float *__restrict__ xs, const float *__res
             }
             __syncthreads();
         }
-        col += C;
     }
 }
 
@@ -111,32 +118,33 @@ __global__ void __launch_bounds__(kWarps * 32)
 bwd_kernel(int V, const Maps m, const float *__restrict__ xs, const float *__restrict__ ys,
            const float *__restrict__ dout, int ld, int col0, float *__restrict__ dxs, float *__restrict__ dys)
 {
-    __shared__ Corner corners[kMaxMaps][kVertsPerCta];
+    __shared__ Corner corners[kVertsPerCta];
     __shared__ float tile[kVertsPerCta][33];
     __shared__ float gx[kWarps][kVertsPerCta], gy[kWarps][kVertsPerCta];
-    __shared__ unsigned char passx[kMaxMaps][kVertsPerCta], passy[kMaxMaps][kVertsPerCta];
+    __shared__ unsigned char passx[kVertsPerCta], passy[kVertsPerCta];
     const int b = blockIdx.y, v0 = blockIdx.x * kVertsPerCta;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int q = threadIdx.x; q < m.n * kVertsPerCta; q += kWarps * 32) {
-        const int k = q / kVertsPerCta, j = q - k * kVertsPerCta;
-        const int v = min(v0 + j, V - 1);
+    const int k = m.chunk_map[blockIdx.z];
+    const int c_lo = (int)m.chunk_c0[blockIdx.z] * kChunk;
+    if (threadIdx.x < kVertsPerCta) {
+        const int v = min(v0 + (int)threadIdx.x, V - 1);
         bool px, py;
-        corners[k][j] = make_corner(xs[(size_t)b * V + v], ys[(size_t)b * V + v], m.dim[k], &px, &py);
-        passx[k][j] = px, passy[k][j] = py;
+        corners[threadIdx.x] = make_corner(xs[(size_t)b * V + v], ys[(size_t)b * V + v], m.dim[k], &px, &py);
+        passx[threadIdx.x] = px, passy[threadIdx.x] = py;
     }
     __syncthreads();
     const bool live = v0 + lane < V;
     float ax = 0.f, ay = 0.f;  // this lane's vertex, this warp's channels
-    int col = col0;
-    for (int k = 0; k < m.n; ++k) {
-        const int C = m.channels[k], plane = m.dim[k] * m.dim[k];
+    {
+        const int C = m.channels[k], plane = m.dim[k] * m.dim[k], col = m.col[k] + col0;
+        const int c_hi = min(C, c_lo + kChunk);
         const size_t boff = (size_t)b * C * plane;
         const float *base = m.ptr[k] ? m.ptr[k] + boff : nullptr;
         float *gbase = m.grad[k] ? m.grad[k] + boff : nullptr;
-        const Corner c = corners[k][lane];
+        const Corner c = corners[lane];
         const float fd = (float)m.dim[k];
-        const float sx = passx[k][lane] ? fd : 0.f, sy = passy[k][lane] ? fd : 0.f;  // d(cx)/d(xs), d(cy)/d(ys)
-        for (int cb = 0; cb < C; cb += 32) {
+        const float sx = passx[lane] ? fd : 0.f, sy = passy[lane] ? fd : 0.f;  // d(cx)/d(xs), d(cy)/d(ys)
+        for (int cb = c_lo; cb < c_hi; cb += 32) {
             // coalesced read of the 32 x 32 gradient tile
 #pragma unroll
             for (int i = 0; i < kVertsPerCta / kWarps; ++i) {
@@ -167,17 +175,16 @@ bwd_kernel(int V, const Maps m, const float *__restrict__ xs, const float *__res
             }
             __syncthreads();
         }
-        col += C;
     }
-    if (dxs || dys) {
+    if (dxs || dys) {  // partial sums of this channel chunk: the outputs were zeroed by the launcher
         gx[warp][lane] = ax, gy[warp][lane] = ay;
         __syncthreads();
         if (warp == 0 && live) {
             float tx = 0.f, ty = 0.f;
 #pragma unroll
             for (int w = 0; w < kWarps; ++w) tx += gx[w][lane], ty += gy[w][lane];
-            if (dxs) dxs[(size_t)b * V + v0 + lane] = tx;
-            if (dys) dys[(size_t)b * V + v0 + lane] = ty;
+            if (dxs) atomicAdd(&dxs[(size_t)b * V + v0 + lane], tx);
+            if (dys) atomicAdd(&dys[(size_t)b * V + v0 + lane], ty);
         }
     }
 }
@@ -199,6 +206,18 @@ static int fill(Maps &m, int n_maps, const float *const *maps, float *const *gra
         }
     }
     *total_channels = tc;
+    m.n_chunks = 0;
+    int col = 0;
+    for (int k = 0; k < n_maps; ++k) {
+        m.col[k] = col;
+        col += channels[k];
+        for (int c0 = 0; c0 < channels[k]; c0 += kChunk) {
+            if (m.n_chunks == kMaxChunks || c0 / kChunk > 65535) return GEOM_ERR_INVALID_ARG;  // > 8192 channels in total
+            m.chunk_map[m.n_chunks] = (unsigned char)k;
+            m.chunk_c0[m.n_chunks] = (unsigned short)(c0 / kChunk);
+            ++m.n_chunks;
+        }
+    }
     return GEOM_OK;
 }
 
@@ -222,7 +241,7 @@ extern "C" int geom_pool_fwd(int b, int V, int n_maps, const float *const *maps,
     cudaStream_t st = (cudaStream_t)stream;
     {
         prof::Scope ps(st, prof::kPoolFwd);
-        pool::fwd_kernel<<<dim3((unsigned)((V + pool::kVertsPerCta - 1) / pool::kVertsPerCta), (unsigned)b), pool::kWarps * 32, 0, st>>>(
+        pool::fwd_kernel<<<dim3((unsigned)((V + pool::kVertsPerCta - 1) / pool::kVertsPerCta), (unsigned)b, (unsigned)m.n_chunks), pool::kWarps * 32, 0, st>>>(
             V, m, xs, ys, out, ld, col0);
     }
     return status_from_cuda(cudaGetLastError());
@@ -248,8 +267,12 @@ extern "C" int geom_pool_bwd(int b, int V, int n_maps, const float *const *maps,
     if (!xs || !ys || !grad_out || col0 + tc > ld || b > 65535) return GEOM_ERR_INVALID_ARG;
     if ((grad_xs || grad_ys) && !maps) return GEOM_ERR_INVALID_ARG;
     {
+        cudaError_t e = cudaSuccess;
+        if (grad_xs) e = cudaMemsetAsync(grad_xs, 0, sizeof(float) * (size_t)b * V, st);
+        if (e == cudaSuccess && grad_ys) e = cudaMemsetAsync(grad_ys, 0, sizeof(float) * (size_t)b * V, st);
+        if (e != cudaSuccess) return status_from_cuda(e);
         prof::Scope ps(st, prof::kPoolBwd);
-        pool::bwd_kernel<<<dim3((unsigned)((V + pool::kVertsPerCta - 1) / pool::kVertsPerCta), (unsigned)b), pool::kWarps * 32, 0, st>>>(
+        pool::bwd_kernel<<<dim3((unsigned)((V + pool::kVertsPerCta - 1) / pool::kVertsPerCta), (unsigned)b, (unsigned)m.n_chunks), pool::kWarps * 32, 0, st>>>(
             V, m, xs, ys, grad_out, ld, col0, grad_xs, grad_ys);
     }
     return status_from_cuda(cudaGetLastError());

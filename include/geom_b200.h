@@ -102,6 +102,10 @@ GEOM_API int geom_chamfer_fwd(int b, int n, const float *xyz1, int m, const floa
  * device arena reused across calls; create one per calling thread, on the device it should use.
  * This is the end-to-end path bench.py reports as "e2e". */
 typedef struct geom_host_ctx geom_host_ctx;
+/* The slice plan geom_chamfer_fwd_host uses (pure host logic, no device access): slice k covers batch items
+ * lo_of[k]..lo_of[k+1]-1; lo_of must hold 9 ints; returns the number of slices (0 on invalid arguments).  With the
+ * tensor-core search the slices are sized in whole waves of its one-CTA-per-SM grid (1, 2, 3, 3 ... waves). */
+GEOM_API int geom_chamfer_host_plan(int b, int n, int m, int chunks, unsigned flags, int sm_count, int *lo_of);
 GEOM_API int geom_host_ctx_create(geom_host_ctx **out);
 GEOM_API int geom_host_ctx_destroy(geom_host_ctx *ctx);
 GEOM_API int geom_chamfer_fwd_host(geom_host_ctx *ctx, int b, int n, const float *h_xyz1, int m,

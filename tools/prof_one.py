@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Run ONE hot kernel a few times at its BASELINE config so ncu can capture it:
-    ncu --set full -k regex:<kernel> -s 2 -c 1 ... python tools/prof_one.py chamfer|tri|gcn|gcn482|sample|loss"""
+    ncu --set full -k regex:<kernel> -s 2 -c 1 ... python tools/prof_one.py chamfer|tri|gcn|gcn482|sample|pool|loss"""
 import os
 import sys
 
@@ -36,6 +36,12 @@ elif what == "sample":
     vi, fi = synth.icosphere(4)
     verts, fi = synth.mesh_batch(vi, 32).to(dev), fi.to(dev)
     fn = lambda: U.batch_sample(verts, fi, 10000)
+elif what == "pool":
+    vs, _ = synth.uv_sphere(32, 15)
+    pv = synth.mesh_batch(vs, 16).to(dev)
+    info = torch.stack((torch.rand(16, device=dev) * 360., 25. + 5. * torch.rand(16, device=dev), 0.6 + 0.4 * torch.rand(16, device=dev)), dim=1)
+    maps = [torch.randn(16, c, d, d, device=dev) for c, d in ((64, 56), (128, 28), (256, 14), (512, 7))]
+    fn = lambda: U.batched_pooling(maps, pv, info)
 elif what == "loss":
     vs, fs = synth.uv_sphere(32, 15)
     pv, fs = synth.mesh_batch(vs, 16).to(dev).requires_grad_(True), fs.to(dev)
