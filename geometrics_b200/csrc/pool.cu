@@ -277,3 +277,115 @@ extern "C" int geom_pool_bwd(int b, int V, int n_maps, const float *const *maps,
     }
     return status_from_cuda(cudaGetLastError());
 }
+
+// ------------------------------------------------------------------------------------------------------
+// Projection of the vertices into the image (batch_camera_info + utils.py:319-330) as ONE launch instead of
+// ~30 tiny (B,3) / (B,V) torch kernels.  Same expressions in the same order as the reference; torch's own
+// kernels may contract a*b - c*d differently, so this path matches the torch expression to fp32 rounding
+// (~1e-6 relative), not bit for bit.  img_info rows are (azimuth deg, elevation deg, distance).
+// ------------------------------------------------------------------------------------------------------
+namespace geom {
+namespace pool {
+
+struct Camera {
+    float c[3];      // position
+    float ax[3], ay[3], az[3];  // rows of cam_mat
+};
+
+__device__ __forceinline__ float rem360(float x)  // torch's % on floats: result takes the sign of the divisor
+{
+    float r = fmodf(x, 360.f);
+    if (r != 0.f && r < 0.f) r += 360.f;
+    return r;
+}
+
+__device__ __forceinline__ Camera make_camera(const float *__restrict__ p)
+{
+    const float kPi = 3.14159265358979323846f;
+    const float theta = rem360(p[0] * kPi / 180.f), phi = rem360(p[1] * kPi / 180.f);
+    Camera k;
+    const float t = p[2] * cosf(phi);
+    k.c[0] = t * cosf(theta), k.c[1] = p[2] * sinf(phi), k.c[2] = t * sinf(theta);
+    // axisX = cross((0,1,0), c) = (c.z, 0, -c.x);  axisY = cross(c, axisX);  axisZ = c;  each normalised
+    float x[3] = {k.c[2], 0.f, -k.c[0]};
+    float y[3] = {k.c[1] * x[2] - k.c[2] * x[1], k.c[2] * x[0] - k.c[0] * x[2], k.c[0] * x[1] - k.c[1] * x[0]};
+    const float nx = sqrtf(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+    const float ny = sqrtf(y[0] * y[0] + y[1] * y[1] + y[2] * y[2]);
+    const float nz = sqrtf(k.c[0] * k.c[0] + k.c[1] * k.c[1] + k.c[2] * k.c[2]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) k.ax[i] = x[i] / nx, k.ay[i] = y[i] / ny, k.az[i] = k.c[i] / nz;
+    return k;
+}
+
+__global__ void __launch_bounds__(256)
+project_fwd_kernel(int V, const float *__restrict__ verts, const float *__restrict__ info, float *__restrict__ xs,
+                   float *__restrict__ ys)
+{
+    const int b = blockIdx.y, v = blockIdx.x * 256 + threadIdx.x;
+    if (v >= V) return;
+    const Camera k = make_camera(info + 3 * b);
+    const float *p = verts + ((size_t)b * V + v) * 3;
+    const float q0 = p[0] * .57f - k.c[0], q1 = p[1] * .57f - k.c[1], q2 = p[2] * .57f - k.c[2];
+    const float X = q0 * k.ax[0] + q1 * k.ax[1] + q2 * k.ax[2];
+    const float Y = q0 * k.ay[0] + q1 * k.ay[1] + q2 * k.ay[2];
+    const float Z = q0 * k.az[0] + q1 * k.az[1] + q2 * k.az[2];
+    const float h = (-Y) / (-Z) * 248.f + 112.f;
+    const float w = X / (-Z) * 248.f + 112.f;
+    xs[(size_t)b * V + v] = h / 223.f;
+    ys[(size_t)b * V + v] = w / 223.f;
+}
+
+// d(verts) from d(xs), d(ys):  xs = (248 Y/Z + 112)/223,  ys = (-248 X/Z + 112)/223,  (X,Y,Z) = M (0.57 p - c)
+__global__ void __launch_bounds__(256)
+project_bwd_kernel(int V, const float *__restrict__ verts, const float *__restrict__ info, const float *__restrict__ gxs,
+                   const float *__restrict__ gys, float *__restrict__ gverts)
+{
+    const int b = blockIdx.y, v = blockIdx.x * 256 + threadIdx.x;
+    if (v >= V) return;
+    const Camera k = make_camera(info + 3 * b);
+    const float *p = verts + ((size_t)b * V + v) * 3;
+    const float q0 = p[0] * .57f - k.c[0], q1 = p[1] * .57f - k.c[1], q2 = p[2] * .57f - k.c[2];
+    const float X = q0 * k.ax[0] + q1 * k.ax[1] + q2 * k.ax[2];
+    const float Y = q0 * k.ay[0] + q1 * k.ay[1] + q2 * k.ay[2];
+    const float Z = q0 * k.az[0] + q1 * k.az[1] + q2 * k.az[2];
+    const float s = 248.f / 223.f;
+    const float gx = gxs ? gxs[(size_t)b * V + v] : 0.f, gy = gys ? gys[(size_t)b * V + v] : 0.f;
+    const float dX = -gy * s / Z;
+    const float dY = gx * s / Z;
+    const float dZ = (-gx * Y + gy * X) * s / (Z * Z);
+    float *g = gverts + ((size_t)b * V + v) * 3;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) g[i] = .57f * (dX * k.ax[i] + dY * k.ay[i] + dZ * k.az[i]);
+}
+
+}  // namespace pool
+}  // namespace geom
+
+extern "C" int geom_project_fwd(int b, int V, const float *verts, const float *img_info, float *xs, float *ys,
+                                geom_stream_t stream)
+{
+    if (b < 0 || V < 0) return GEOM_ERR_INVALID_ARG;
+    if (b == 0 || V == 0) return GEOM_OK;
+    if (!verts || !img_info || !xs || !ys || b > 65535) return GEOM_ERR_INVALID_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    {
+        geom::prof::Scope ps(st, geom::prof::kMisc);
+        geom::pool::project_fwd_kernel<<<dim3((unsigned)((V + 255) / 256), (unsigned)b), 256, 0, st>>>(V, verts, img_info, xs, ys);
+    }
+    return geom::status_from_cuda(cudaGetLastError());
+}
+
+extern "C" int geom_project_bwd(int b, int V, const float *verts, const float *img_info, const float *grad_xs,
+                                const float *grad_ys, float *grad_verts, geom_stream_t stream)
+{
+    if (b < 0 || V < 0) return GEOM_ERR_INVALID_ARG;
+    if (b == 0 || V == 0) return GEOM_OK;
+    if (!verts || !img_info || !grad_verts || b > 65535) return GEOM_ERR_INVALID_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    {
+        geom::prof::Scope ps(st, geom::prof::kMisc);
+        geom::pool::project_bwd_kernel<<<dim3((unsigned)((V + 255) / 256), (unsigned)b), 256, 0, st>>>(V, verts, img_info, grad_xs, grad_ys,
+                                                                                                    grad_verts);
+    }
+    return geom::status_from_cuda(cudaGetLastError());
+}

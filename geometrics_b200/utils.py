@@ -386,8 +386,50 @@ def batch_camera_info(param: torch.Tensor):
     return cam_mat, cam_pos
 
 
+class ProjectFunction(torch.autograd.Function):
+    """(verts (B,V,3), img_info (B,3)) -> (xs, ys): geom_project_fwd / geom_project_bwd (one launch each)."""
+
+    @staticmethod
+    def forward(ctx, verts, img_info):
+        L = _lib.lib()
+        vc, ic = verts.detach().contiguous(), img_info.detach().contiguous()
+        b, v, _ = vc.shape
+        dev = vc.device
+        with torch.cuda.device(dev):
+            xs = torch.empty((b, v), dtype=torch.float32, device=dev)
+            ys = torch.empty((b, v), dtype=torch.float32, device=dev)
+            _lib.check(L.geom_project_fwd(b, v, vc.data_ptr(), ic.data_ptr(), xs.data_ptr(), ys.data_ptr(),
+                                          _lib.current_stream_ptr(dev)), "geom_project_fwd")
+        ctx.save_for_backward(vc, ic)
+        return xs, ys
+
+    @staticmethod
+    def backward(ctx, gxs, gys):
+        L = _lib.lib()
+        vc, ic = ctx.saved_tensors
+        b, v, _ = vc.shape
+        dev = vc.device
+        gxs = gxs.contiguous() if gxs is not None else None
+        gys = gys.contiguous() if gys is not None else None
+        with torch.cuda.device(dev):
+            gv = torch.empty_like(vc)
+            _lib.check(L.geom_project_bwd(b, v, vc.data_ptr(), ic.data_ptr(), gxs.data_ptr() if gxs is not None else None,
+                                          gys.data_ptr() if gys is not None else None, gv.data_ptr(),
+                                          _lib.current_stream_ptr(dev)), "geom_project_bwd")
+        return gv, None
+
+
+FUSED_PROJECTION = True  # project_vertices on CUDA fp32 inputs: one kernel instead of ~30 (B,3)/(B,V) torch ops
+
+
 def project_vertices(verts_pos: torch.Tensor, img_info: torch.Tensor):
-    """utils.py:319-330: image-plane coordinates of the vertices as fractions of the image size -> (xs, ys), (B,V)."""
+    """utils.py:319-330: image-plane coordinates of the vertices as fractions of the image size -> (xs, ys), (B,V).
+    CUDA fp32 inputs take the fused kernel (equal to the torch expression below to fp32 rounding); anything else,
+    or an ``img_info`` that requires grad, evaluates the reference's expression with torch ops."""
+    if (FUSED_PROJECTION and verts_pos.is_cuda and img_info.is_cuda and verts_pos.dtype == torch.float32
+            and img_info.dtype == torch.float32 and verts_pos.dim() == 3 and verts_pos.shape[-1] == 3
+            and tuple(img_info.shape) == (verts_pos.shape[0], 3) and not img_info.requires_grad):
+        return ProjectFunction.apply(verts_pos, img_info)
     cam_mat, cam_pos = batch_camera_info(img_info)
     pt = torch.matmul((verts_pos * .57) - cam_pos.unsqueeze(1), cam_mat.permute(0, 2, 1))
     x, y, z = pt[:, :, 0], pt[:, :, 1], pt[:, :, 2]

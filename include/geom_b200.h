@@ -207,6 +207,15 @@ GEOM_API int geom_sample_bwd(int b, int V, int F, const int64_t *faces, int num,
  *   NULL), grad_xs / grad_ys (B,V) = gradient through the bilinear weights (either may be NULL); floor, ceil and
  *   clamp carry torch's gradients (0, 0, pass-through inside [0, dim-1]).
  * ------------------------------------------------------------------------------------------- */
+/* geom_project_fwd / _bwd: the projection feeding the pooling (batch_camera_info, utils.py:283-312, and
+ * utils.py:319-330) in one launch: img_info (B,3) rows are (azimuth deg, elevation deg, distance); xs, ys (B,V) are
+ * the image coordinates as fractions of the image size.  Same expressions and order as the reference; equal to the
+ * torch expression to fp32 rounding (torch's kernels may contract differently).  _bwd: grad_verts (B,V,3) overwritten
+ * (img_info is data and gets no gradient); grad_xs / grad_ys may be NULL. */
+GEOM_API int geom_project_fwd(int b, int V, const float *verts, const float *img_info, float *xs, float *ys,
+                     geom_stream_t stream);
+GEOM_API int geom_project_bwd(int b, int V, const float *verts, const float *img_info, const float *grad_xs,
+                     const float *grad_ys, float *grad_verts, geom_stream_t stream);
 GEOM_API int geom_pool_fwd(int b, int V, int n_maps, const float *const *maps, const int *channels, const int *dims,
                   const float *xs, const float *ys, float *out, int ld, int col0, geom_stream_t stream);
 GEOM_API int geom_pool_bwd(int b, int V, int n_maps, const float *const *maps, float *const *grad_maps,

@@ -122,7 +122,7 @@ def batch_camera_info(param):
     cam_z = temp * torch.sin(theta)
     cam_pos = torch.cat((cam_x.unsqueeze(1), cam_y.unsqueeze(1), cam_z.unsqueeze(1)), dim=1)
     axis_z = cam_pos.clone()
-    axis_y = torch.tensor([0., 1., 0.], device=param.device).unsqueeze(0).expand(axis_z.shape[0], 3)
+    axis_y = torch.tensor([0., 1., 0.], dtype=param.dtype, device=param.device).unsqueeze(0).expand(axis_z.shape[0], 3)
     axis_x = torch.linalg.cross(axis_y, axis_z, dim=1)
     axis_y = torch.linalg.cross(axis_z, axis_x, dim=1)
     axis_x = axis_x / torch.sqrt(torch.sum(axis_x ** 2, dim=1)).unsqueeze(-1)

@@ -28,7 +28,7 @@ def test_forward_bit_exact_vs_reference_golden(cuda):
 
 @pytest.mark.parametrize("shape", [(2, 96, ((5, 56), (7, 28), (33, 14), (40, 7))), (3, 482, ((64, 56), (128, 28), (256, 14), (512, 7))),
                                    (1, 31, ((3, 9),)), (2, 33, ((1, 5), (70, 3)))])
-def test_forward_and_backward_vs_torch(cuda, shape):
+def test_forward_and_backward_vs_torch(cuda, shape, monkeypatch):
     import geometrics_b200.utils as U
 
     b, v, maps = shape
@@ -47,11 +47,39 @@ def test_forward_and_backward_vs_torch(cuda, shape):
         (f * up).sum().backward()
         res.append((f.detach(), p.grad, [x.grad for x in bl]))
     (f0, dp0, db0), (f1, dp1, db1) = res
-    assert torch.equal(f0, f1), f"forward differs: {float((f0 - f1).abs().max())}"
+    # the fused projection equals torch's to fp32 rounding, the bilinear gather is continuous in the coordinates
+    assert float((f0 - f1).abs().max()) <= 2e-4 * float(f1.abs().max()), f"forward differs: {float((f0 - f1).abs().max())}"
+    # d(features)/d(position) is piecewise constant in the texel cell: a coordinate within rounding of a texel
+    # boundary may sit in the neighbouring cell on one of the two paths, so allow a handful of outlier vertices
     scale = float(dp1.abs().max())
-    assert float((dp0 - dp1).abs().max()) <= 2e-4 * scale, (float((dp0 - dp1).abs().max()), scale)
+    outliers = ((dp0 - dp1).abs().amax(dim=-1) > 1e-3 * scale).float().mean()
+    assert float(outliers) <= 0.005, (float(outliers), float((dp0 - dp1).abs().max()), scale)
     for a, r in zip(db0, db1):
-        assert float((a - r).abs().max()) <= 1e-5 * max(1.0, float(r.abs().max()))
+        assert float((a - r).abs().max()) <= 2e-4 * max(1.0, float(r.abs().max()))
+    # given the SAME projected coordinates the gather is bit-identical to the torch expression
+    xs, ys = R.project_vertices(verts.to(cuda), img_info)
+    assert torch.equal(U.pool_features(blocks, xs, ys), R.pool_features(blocks, xs, ys))
+    monkeypatch.setattr(U, "FUSED_PROJECTION", False)
+    assert torch.equal(U.batched_pooling(blocks, verts.to(cuda), img_info), R.batched_pooling(blocks, verts.to(cuda), img_info))
+
+
+def test_fused_projection_vs_torch(cuda):
+    """geom_project_fwd / _bwd against the reference expression evaluated by torch on the same device."""
+    import geometrics_b200.utils as U
+
+    g = torch.Generator().manual_seed(9)
+    verts = (torch.rand(5, 700, 3, generator=g) - 0.5).to(cuda)
+    info = torch.stack((torch.rand(5, generator=g) * 720. - 180., 25. + 5. * torch.rand(5, generator=g),
+                        0.6 + 0.4 * torch.rand(5, generator=g)), dim=1).to(cuda)
+    gx, gy = torch.randn(5, 700, generator=g).to(cuda), torch.randn(5, 700, generator=g).to(cuda)
+    out = []
+    for fn in (U.project_vertices, R.project_vertices):
+        p = verts.clone().requires_grad_(True)
+        xs, ys = fn(p, info)
+        (xs * gx + ys * gy).sum().backward()
+        out.append((xs.detach(), ys.detach(), p.grad))
+    for a, r in zip(*out):
+        assert float((a - r).abs().max()) <= 2e-5 * max(1.0, float(r.abs().max())), float((a - r).abs().max())
 
 
 def test_gather_into_block_input_buffer(cuda):

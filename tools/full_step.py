@@ -7,8 +7,9 @@ sharded over GPUs with DDP (one process per GPU, launched with torchrun).
     python tools/full_step.py [--batch 32] [--steps 10] [--impl ours|torch] [--latent] [--sync-bn]
     torchrun --nproc-per-node 8 tools/full_step.py --batch 32      # global batch 32, 4 per rank
 
-The image encoder and `batched_pooling` are out of scope for the library (stock cuDNN convs; SURVEY
-8f-1), so they are restated here in plain torch only to make the step runnable.  `--impl torch` swaps
+The image encoder is out of scope for the library (stock cuDNN convs), so it is restated here in plain torch
+only to make the step runnable; `batched_pooling` is served by the library (csrc/pool.cu) and by the
+plain-torch restatement below in the comparison arm.  `--impl torch` swaps
 the hot path for the reference's torch expressions (tests/ref_torch.py) and, when
 oracle/_ref/libref_cuda.so travelled along, the reference's own .cu kernels: the comparison arm.
 HARNESS / BENCH INFRASTRUCTURE, not part of the product path.
@@ -178,6 +179,7 @@ def main():
     opt = torch.optim.Adam(params, lr=1e-4)
 
     surface, lap, note = U.batch_point_to_surface, U.batch_get_lap_info, "geometrics_b200 kernels"
+    pooling = U.batched_pooling if args.impl != "torch" else batched_pooling
     orig_gcn = g.layers.zeron_gcn
     if args.impl == "torch":
         surface, lap, dense_gcn, dense_adj, note = reference_ops(dev)
@@ -195,13 +197,13 @@ def main():
         opt.zero_grad(set_to_none=True)
         ipb = init_pos.unsqueeze(0).expand(bsz, V, 3)
         f1_, f2_, f3_ = (e(images) for e in encoders)
-        vf = batched_pooling(f1_, ipb, img_info)
+        vf = pooling(f1_, ipb.contiguous(), img_info)
         vf, p1 = blocks[0](ipb, vf, adj_info["adj"])
         p1 = ipb + p1
-        vf = torch.cat((vf, batched_pooling(f2_, p1, img_info)), dim=-1)
+        vf = torch.cat((vf, pooling(f2_, p1, img_info)), dim=-1)
         vf, p2 = blocks[1](p1, vf, adj_info["adj"])
         p2 = p2 + p1
-        vf = torch.cat((vf, batched_pooling(f3_, p2, img_info)), dim=-1)
+        vf = torch.cat((vf, pooling(f3_, p2, img_info)), dim=-1)
         _, p3 = blocks[2](p2, vf, adj_info["adj"])
         p3 = p3 + p2
         s1 = surface(p1, adj_info, gt, num=args.samples)
