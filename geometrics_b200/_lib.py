@@ -47,6 +47,8 @@ SYMBOLS = {
     "geom_face_areas": (_i, [_i, _i, _vp, _i, _vp, _vp, _i, _vp]),
     "geom_sample_fwd": (_i, [_i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "geom_sample_bwd": (_i, [_i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "geom_edge_loss_fwd": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp]),
+    "geom_edge_loss_bwd": (_i, [_i, _i, _vp, _i, _vp, _vp, C.c_float, _vp, _vp]),
     "geom_project_fwd": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp]),
     "geom_project_bwd": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "geom_pool_fwd": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),

@@ -330,9 +330,45 @@ def batch_point_to_surface(pred_vert, adj_info, gt_points, num=1000, f1=False, g
 # ------------------------------------------------------------------------------------------------
 # regularisers
 # ------------------------------------------------------------------------------------------------
+class EdgeLossFunction(torch.autograd.Function):
+    """verts (B,V,3), faces (F,3) int64 -> scalar mean squared edge length: geom_edge_loss_fwd / _bwd."""
+
+    @staticmethod
+    def forward(ctx, verts, faces):
+        L = _lib.lib()
+        vc = verts.detach().contiguous()
+        b, v, _ = vc.shape
+        f = faces.shape[0]
+        dev = vc.device
+        with torch.cuda.device(dev):
+            acc = torch.empty(1, dtype=torch.float64, device=dev)
+            _lib.check(L.geom_edge_loss_fwd(b, v, vc.data_ptr(), f, faces.data_ptr(), acc.data_ptr(),
+                                            _lib.current_stream_ptr(dev)), "geom_edge_loss_fwd")
+        ctx.save_for_backward(vc, faces)
+        ctx.scale = 1.0 / (3.0 * b * f) if b * f else 0.0
+        return (acc * ctx.scale).to(torch.float32).reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        L = _lib.lib()
+        vc, faces = ctx.saved_tensors
+        b, v, _ = vc.shape
+        dev = vc.device
+        gc = g.detach().to(torch.float32).contiguous()
+        with torch.cuda.device(dev):
+            gv = torch.empty_like(vc)
+            _lib.check(L.geom_edge_loss_bwd(b, v, vc.data_ptr(), faces.shape[0], faces.data_ptr(), gc.data_ptr(), ctx.scale,
+                                            gv.data_ptr(), _lib.current_stream_ptr(dev)), "geom_edge_loss_bwd")
+        return gv, None
+
+
 def batch_calc_edge(verts, info):
-    """Mean squared edge length over the three edges of every face (utils.py:636-651); plain torch."""
+    """Mean squared edge length over the three edges of every face (utils.py:636-651).  CUDA fp32 (B,V,3) input: one
+    fused kernel each way (fp64 accumulation; equal to the torch expression to fp32 rounding); otherwise the
+    reference's torch expression."""
     faces = info["faces"]
+    if verts.is_cuda and verts.dtype == torch.float32 and verts.dim() == 3 and verts.shape[-1] == 3 and faces.numel() > 0:
+        return EdgeLossFunction.apply(verts, _faces_i64(faces, verts.device))
     p1 = torch.index_select(verts, 1, faces[:, 0])
     p2 = torch.index_select(verts, 1, faces[:, 1])
     p3 = torch.index_select(verts, 1, faces[:, 2])

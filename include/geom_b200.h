@@ -207,6 +207,14 @@ GEOM_API int geom_sample_bwd(int b, int V, int F, const int64_t *faces, int num,
  *   NULL), grad_xs / grad_ys (B,V) = gradient through the bilinear weights (either may be NULL); floor, ceil and
  *   clamp carry torch's gradients (0, 0, pass-through inside [0, dim-1]).
  * ------------------------------------------------------------------------------------------- */
+/* Edge-length regulariser (replaces batch_calc_edge, utils.py:636-651).
+ * geom_edge_loss_fwd: *sum (device double, overwritten) = sum over the B*F faces of |p2-p1|^2 + |p3-p1|^2 + |p2-p3|^2;
+ *   the reference's value is sum / (3*B*F).
+ * geom_edge_loss_bwd: grad_verts (B,V,3, overwritten) = *grad_scalar * scale * d(sum)/d(verts); grad_scalar is a
+ *   DEVICE scalar (the upstream gradient), scale the host-side 1/(3*B*F). */
+GEOM_API int geom_edge_loss_fwd(int b, int V, const float *verts, int F, const int64_t *faces, double *sum, geom_stream_t stream);
+GEOM_API int geom_edge_loss_bwd(int b, int V, const float *verts, int F, const int64_t *faces, const float *grad_scalar,
+                       float scale, float *grad_verts, geom_stream_t stream);
 /* geom_project_fwd / _bwd: the projection feeding the pooling (batch_camera_info, utils.py:283-312, and
  * utils.py:319-330) in one launch: img_info (B,3) rows are (azimuth deg, elevation deg, distance); xs, ys (B,V) are
  * the image coordinates as fractions of the image size.  Same expressions and order as the reference; equal to the

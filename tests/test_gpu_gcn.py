@@ -224,6 +224,33 @@ def test_regularisers_vs_torch(cuda):
     assert e.shape == () and float(e) > 0
 
 
+@pytest.mark.parametrize("b", [1, 4, 33])
+def test_edge_regulariser_vs_torch(cuda, b):
+    """geom_edge_loss_fwd / _bwd against the reference expression utils.py:636-651, forward and gradient."""
+    import geometrics_b200 as g
+    import geometrics_b200.utils as U
+    from geometrics_b200 import synth
+
+    verts, faces = synth.uv_sphere(32, 15)
+    info = {"faces": faces.to(cuda)}
+    outs = []
+    for fused in (True, False):
+        p = (synth.mesh_batch(verts, b) * 1.3).to(cuda).requires_grad_(True)
+        if fused:
+            e = U.batch_calc_edge(p, info)
+        else:
+            f = info["faces"]
+            p1, p2, p3 = (torch.index_select(p, 1, f[:, k]) for k in range(3))
+            e1, e2, e3 = p2 - p1, p3 - p1, p2 - p3
+            e = (torch.sum(e1 ** 2, -1).mean() + torch.sum(e2 ** 2, -1).mean() + torch.sum(e3 ** 2, -1).mean()) / 3.
+        (e * 300.).backward()
+        outs.append((e.detach(), p.grad))
+    (e0, g0), (e1_, g1) = outs
+    assert e0.shape == () and e0.dtype == torch.float32
+    assert abs(float(e0) - float(e1_)) <= 2e-6 * abs(float(e1_))
+    assert float((g0 - g1).abs().max()) <= 1e-5 * float(g1.abs().max())
+
+
 @pytest.mark.parametrize("shape", [(3, 482, 963, 192, 3), (2, 642, 256, 256, 3), (2, 482, 192, 192, 3), (2, 482, 210, 250, 10),
                                    (2, 100, 37, 50, 10), (1, 482, 1155, 192, 3), (4, 2562, 256, 256, 3), (1, 130, 8, 16, 3)])
 def test_tensor_gemm_layer_vs_torch(cuda, shape):
