@@ -39,7 +39,7 @@ def prof(fn):
     return {k.split("::", 1)[1]: round(v[0] / v[1], 5) for k, v in _lib.prof_end().items()}
 
 
-out = {"B": B, "N": N, "M": M, "legacy_env": bool(os.environ.get("GEOM_TC_LEGACY"))}
+out = {"B": B, "N": N, "M": M}
 for name, kw in (("fp32", {"tensor": False}), ("tensor", {"tensor": True})):
     f = lambda i: g.chamfer_forward(*xs[i % ring], want_dist=False, **kw)
     ms = timeit(f)
