@@ -339,6 +339,9 @@ def run_product(args):
                         "traffic": traffic, "traffic_source": traffic_src,
                         "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1650 TFLOP/s",
                         "kernel": dom_name, "kernel_ms": dom_ms, "flops_per_launch": mma_flops,
+                        # SURVEY.md 8d's algorithmic figure: 8 flop per distance evaluation, 2*B*n*m evaluations
+                        "algorithmic_flops_per_launch": 16 * B * N_PTS * M_PTS,
+                        "algorithmic_tflops": 16 * B * N_PTS * M_PTS / (dom_ms * 1e-3) / 1e12,
                         "note": "flops = issued tcgen05.mma shapes (K=16 carries the 15-term split distance); the kernel is "
                                 "bound by the TMEM accumulator round trip and the ALU-pipe minima, not by HBM (see DESIGN.md 4.1)",
                         "hbm": hbm,
