@@ -175,7 +175,8 @@ __device__ __forceinline__ void tma_load(void *smem_dst, const void *gmem_src, u
 struct ScanSmem {
     uint4 sA[kGroups][2][128];           // [row block][k-chunk][row]  canonical no-swizzle K-major
     uint4 sB[kStages][2][kTileCols];     // [stage][k-chunk][row]
-    float4 evm[kEvCap][kScanThreads];    // events: the four 32-candidate block minima of a listed tile ...
+    uint4 evm[kEvCap][kScanThreads];     // events: the four 32-candidate block minima of a listed tile (float bits; the
+                                         // flush reuses the slots for block ids, so every access is through unsigned) ...
     unsigned evt[kEvCap][kScanThreads];  // ... and the tile index
     unsigned long long full_bar[kGroups][2], empty_bar[kGroups][2];  // accumulator hand-over, per group and half
     unsigned long long b_full[kStages], b_free[kStages];             // ring stage landed / no longer read
@@ -292,7 +293,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 bot
         const float eps2 = (rmax < 1.0e15f) ? 2.0f * both.eps_scale * rmax * rmax : __int_as_float(0x7f800000);
         const float *cb = a.cxyz + (size_t)bi * a.nc_full * 3;
         const bool vec_ok = (((uintptr_t)cb) & 15u) == 0;
-        float4 *evm = &S.evm[0][tid];
+        uint4 *evm = &S.evm[0][tid];
         unsigned *evt = &S.evt[0][tid];
 
         // Exact re-evaluation of the listed tiles' 32-candidate blocks that are still inside the window.
@@ -301,14 +302,14 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 bot
         // max-over-lanes(survivors) block evaluations per warp.
         auto flush = [&]() {
             const float thr = mt + eps2;
-            unsigned *blk = reinterpret_cast<unsigned *>(&S.evm[0][0]);  // survivors: reuse evm[e][tid] as 4 x u32
+            unsigned *blk = &S.evm[0][0].x;  // survivors: reuse evm[e][tid] as 4 x u32
             int keep = 0;
             for (int e = 0; e < cnt; ++e) {
-                const float4 m = evm[(size_t)e * kScanThreads];
+                const uint4 mb = evm[(size_t)e * kScanThreads];
                 const unsigned t4 = evt[(size_t)e * kScanThreads] * 4u;
                 // block ids of event e are written into evm[keep >> 2]: keep <= 4 e before the event, and
                 // event e has already been read, so slot (keep >> 2) <= e is free to overwrite
-                const float bms[4] = {m.x, m.y, m.z, m.w};
+                const float bms[4] = {__uint_as_float(mb.x), __uint_as_float(mb.y), __uint_as_float(mb.z), __uint_as_float(mb.w)};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     if (!(bms[i] > thr)) {  // NaN counts as inside
@@ -378,7 +379,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 bot
             mt = m4;
             const float tm = fminf(fminf(bm0, bm1), fminf(bm2, bm3));
             if (!(tm > mt + eps2)) {  // predicated append: the tile holds a candidate inside the window
-                evm[(size_t)cnt * kScanThreads] = make_float4(bm0, bm1, bm2, bm3);
+                evm[(size_t)cnt * kScanThreads] = make_uint4(__float_as_uint(bm0), __float_as_uint(bm1), __float_as_uint(bm2), __float_as_uint(bm3));
                 evt[(size_t)cnt * kScanThreads] = (unsigned)t;
                 ++cnt;
             }
