@@ -19,6 +19,14 @@ GEOM_FLAG_EXACT_TAIL = 1
 GEOM_FLAG_ONEWAY = 2
 GEOM_FLAG_TENSOR = 4
 GEOM_FLAG_FP32 = 8
+# geom_debug_set knobs (tests / tuning only)
+GEOM_DEBUG_TC_EPS_FACTOR = 0
+GEOM_DEBUG_TRI_PR = 1
+GEOM_DEBUG_TRI_CHUNK = 2
+GEOM_DEBUG_TRI_TC_EPS_FACTOR = 3
+GEOM_DEBUG_CHAMFER_VARIANT = 4
+GEOM_DEBUG_CHAMFER_STRIP = 5
+GEOM_DEBUG_CHAMFER_TILE_COLS = 6
 
 # every symbol include/geom_b200.h declares: name -> (restype, argtypes)
 _vp, _i, _u, _sz = C.c_void_p, C.c_int, C.c_uint, C.c_size_t
@@ -39,7 +47,9 @@ SYMBOLS = {
     "geom_chamfer_loss_workspace_bytes": (_sz, [_i, _i, _i]),
     "geom_chamfer_loss_fwd": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "geom_chamfer_loss_bwd": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "geom_debug_set": (_i, [_i, C.c_float]),
     "geom_tri_workspace_bytes": (_sz, [_i, _i]),
+    "geom_tri_tensor_workspace_bytes": (_sz, [_i, _i, _i]),
     "geom_tri_fwd": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _u, _vp]),
     "geom_tri_loss_workspace_bytes": (_sz, [_i, _i]),
     "geom_tri_loss_fwd": (_i, [_i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -98,7 +108,7 @@ def lib() -> C.CDLL:
     return _lib
 
 
-GEOM_PROF_KERNELS = 20
+GEOM_PROF_KERNELS = 26
 
 
 def prof_begin() -> None:

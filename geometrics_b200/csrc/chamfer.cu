@@ -485,13 +485,12 @@ struct Tune {
 static Tune read_tune()
 {
     Tune t = {1, 2, 0};  // phased FP2 order, 256-column tiles, strips of 2 (profiles/r01_chamfer_tune_v2.jsonl)
-    if (const char *e = getenv("GEOM_CHAMFER_TUNE")) {
-        int v = 0, s = 0, tc = 0;
-        const int got = sscanf(e, "%d,%d,%d", &v, &s, &tc);
-        if (got >= 1 && v >= 0 && v < 8) t.variant = v;
-        if (got >= 2 && s >= 1) t.strip = s;
-        if (got >= 3 && tc >= 32) t.tile_cols = tc;
-    }
+    // tuning sweeps (tools/tune_chamfer.py) override through geom_debug_set; knob value v+1 selects variant v
+    const int v = (int)debug::knob(GEOM_DEBUG_CHAMFER_VARIANT), s = (int)debug::knob(GEOM_DEBUG_CHAMFER_STRIP),
+              tc = (int)debug::knob(GEOM_DEBUG_CHAMFER_TILE_COLS);
+    if (v >= 1 && v <= 8) t.variant = v - 1;
+    if (s >= 1) t.strip = s;
+    if (tc >= 32) t.tile_cols = tc;
     return t;
 }
 

@@ -30,14 +30,12 @@
 //      (chamfer_distance.cu:39,47).
 //
 // One launch covers both directions (blockIdx.z); ~0.9 instructions per pair instead of ~10.
-#include <cstdlib>
-
-#include <cuda_bf16.h>
-
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace geom {
 namespace chamfer_tc {
+
+using namespace geom::tc;
 
 constexpr int kGroups = 4;                      // 128-row blocks per CTA == scanner warp groups
 constexpr int kRowsPerCta = 128 * kGroups;
@@ -52,24 +50,6 @@ constexpr int kTmemCols = kGroups * 2 * kHalfCols;
 constexpr unsigned kBlockBytes = 2 * 128 * 16;  // one packed 128-row block
 constexpr float kEpsScale = 2.5e-4f;
 constexpr float kBigNorm = 1.0e30f;  // padding candidates: approximate distance far above anything real
-
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-
-// Shared-memory matrix descriptor: K-major, no swizzle ("interleave"): 8-row x 16-byte core matrices;
-// LBO = byte distance between the two 16-byte k-chunks, SBO = byte distance between 8-row groups.
-__device__ __forceinline__ u64 make_desc(unsigned saddr, unsigned lbo_bytes, unsigned sbo_bytes)
-{
-    u64 d = 0;
-    d |= (u64)((saddr & 0x3FFFFu) >> 4);
-    d |= (u64)((lbo_bytes >> 4) & 0x3FFFu) << 16;
-    d |= (u64)((sbo_bytes >> 4) & 0x3FFFu) << 32;
-    d |= (u64)1 << 46;  // descriptor version 1 (sm_100)
-    return d;
-}
-
-__device__ __forceinline__ unsigned short bf16_bits(float v) { return __bfloat16_as_ushort(__float2bfloat16_rn(v)); }
-__device__ __forceinline__ float bf16_val(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
-__device__ __forceinline__ unsigned pack_bf16x2(float lo, float hi) { return (unsigned)bf16_bits(lo) | ((unsigned)bf16_bits(hi) << 16); }
 
 // Per point: two 16-byte k-chunks per form.
 //   A form (query):      -2ph(3) -2pl(3) -2ph(3)  n1 n2 n3   1  1  1   0
@@ -135,43 +115,6 @@ struct SearchArgs2 {
     float eps_scale;      // kEpsScale (tests shrink it to measure the safety margin)
 };
 
-// 64 consecutive columns of this warp's 32 TMEM lanes: load and wait in ONE statement, so that no use of
-// the registers can be scheduled between the load and its wait.
-__device__ __forceinline__ void tmem_ld64_wait(unsigned (&v)[64], unsigned taddr)
-{
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];\n\ttcgen05.wait::ld.sync.aligned;"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]), "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]), "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
-                 : "r"(taddr)
-                 : "memory");
-}
-
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
-{
-    unsigned done = 0;
-    while (!done) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done)
-                     : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)  // suspend-time hint (ns): park instead of spinning
-                     : "memory");
-    }
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// TMA bulk copy global -> shared, completion counted in bytes on `bar`
-__device__ __forceinline__ void tma_load(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *bar)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
-                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
 struct ScanSmem {
     uint4 sA[kGroups][2][128];           // [row block][k-chunk][row]  canonical no-swizzle K-major
     uint4 sB[kStages][2][kTileCols];     // [stage][k-chunk][row]
@@ -183,20 +126,6 @@ struct ScanSmem {
     unsigned long long a_full;
     unsigned tmem_slot;
 };
-
-// minimum of 32 approximate distances v[o..o+31]: 16 three-input minima as a depth-4 tree
-__device__ __forceinline__ float tree_min32(const unsigned (&v)[64], int o)
-{
-    float l1[12];
-#pragma unroll
-    for (int i = 0; i < 10; ++i)
-        l1[i] = min3(__uint_as_float(v[o + 3 * i]), __uint_as_float(v[o + 3 * i + 1]), __uint_as_float(v[o + 3 * i + 2]));
-    l1[10] = __uint_as_float(v[o + 30]);
-    l1[11] = __uint_as_float(v[o + 31]);
-    const float a0 = min3(l1[0], l1[1], l1[2]), a1 = min3(l1[3], l1[4], l1[5]);
-    const float a2 = min3(l1[6], l1[7], l1[8]), a3 = min3(l1[9], l1[10], l1[11]);
-    return fminf(min3(a0, a1, a2), a3);
-}
 
 __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 both)
 {
@@ -438,10 +367,7 @@ cudaError_t launch(int b, int n, const float *xyz1, int m, const float *xyz2, in
     SearchArgs2 s;
     s.rmax_bits = rmax;
     s.eps_scale = kEpsScale;
-    if (const char *env = getenv("GEOM_TC_EPS_SCALE")) {  // tests only: multiply the filter margin
-        const float f = (float)atof(env);
-        if (f > 0.f) s.eps_scale = kEpsScale * f;
-    }
+    if (const float f = debug::knob(GEOM_DEBUG_TC_EPS_FACTOR); f > 0.f) s.eps_scale = kEpsScale * f;  // tests: margin study
     // direction 0: every xyz1 point over xyz2[0, m_scan);  direction 1: every xyz2 point over xyz1[0, n_scan)
     SearchArgs &d0 = s.dir[0], &d1 = s.dir[1];
     d0.qxyz = xyz1, d0.cxyz = xyz2, d0.formA = a1, d0.formB = b2, d0.dist = dist1, d0.idx = idx1;
@@ -451,13 +377,8 @@ cudaError_t launch(int b, int n, const float *xyz1, int m, const float *xyz2, in
     {
         prof::Scope ps(st, prof::kChamferTcScan);
         const size_t rows = np > mp ? np : mp;
-        static bool smem_set[64] = {};  // per device: opt in to > 48 KB of dynamic shared memory once
-        int dev = 0;
-        if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
-        if (dev < 0 || dev >= 64 || !smem_set[dev]) {
-            if ((e = cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem))) != cudaSuccess) return e;
-            if (dev >= 0 && dev < 64) smem_set[dev] = true;
-        }
+        static std::atomic<unsigned long long> smem_done{0};
+        if ((e = ensure_dynamic_smem(scan_kernel, (int)sizeof(ScanSmem), smem_done)) != cudaSuccess) return e;
         scan_kernel<<<dim3((unsigned)(rows / kRowsPerCta), b, 2), kThreads, sizeof(ScanSmem), st>>>(s);
     }
     return cudaGetLastError();

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/geom_b200.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -116,7 +118,8 @@ namespace prof {
 enum Kernel {
     kChamferTwoWay = 0, kChamferRefine, kChamferOneWay, kTri, kChamferLoss, kChamferLossBwd,
     kSampleFwd, kSampleBwd, kSampleArea, kGcnGemm, kGcnSpmm, kGcnBwd, kTriClosest, kTriClosestBwd,
-    kMisc, kMisc2, kChamferTcScan, kChamferTcPack, kPoolFwd, kPoolBwd, kKernelCount
+    kMisc, kMisc2, kChamferTcScan, kChamferTcPack, kPoolFwd, kPoolBwd, kTriTcScan, kTriTcPrep, kGcnBwdGemm, kBnFwd,
+    kBnBwd, kSpare, kKernelCount
 };
 static_assert(kKernelCount == GEOM_PROF_KERNELS, "geom_b200.h GEOM_PROF_KERNELS out of sync");
 struct Scope {
@@ -135,6 +138,19 @@ cudaError_t launch(int b, int n, const float *xyz1, int m, const float *xyz2, in
                    int zero2, float *dist1, int *idx1, float *dist2, int *idx2, void *workspace, cudaStream_t st);
 }  // namespace chamfer_tc
 
+// tensor-core filtered point-to-triangle search (tri_tc.cu)
+namespace tri_tc {
+size_t workspace_bytes(int b, int n, int m);
+cudaError_t launch(int b, int n, const float *xyz, int m, const float *t1, const float *t2, const float *t3, int m_scan_end,
+                   int exact, int empty_tail, float *dist, int *point, int *index, void *workspace, float eps_factor,
+                   cudaStream_t st);
+}  // namespace tri_tc
+
+// process-wide debug knobs (misc.cu, geom_debug_set): 0 = not set
+namespace debug {
+float knob(int id);
+}
+
 // tensor-core (3xTF32 tcgen05) feature GEMM of the 0N-GCN layer (gcn_tc.cu)
 namespace gcn_tc {
 bool supported(int N);
@@ -142,6 +158,22 @@ size_t workspace_bytes(int K, int N);
 cudaError_t launch(int M, int K, int N, const float *X, const float *W, const float *bias, float *Y, float *T,
                    int ksplit, int ldt, int relu, void *wsplit, cudaStream_t st);
 }  // namespace gcn_tc
+
+// Opt `kernel` in to `bytes` (> 48 KB) of dynamic shared memory, once per device.  `done` is the caller's function-local
+// static bit set (one bit per device ordinal < 64); atomic, so concurrent callers are safe -- at worst the idempotent
+// attribute call runs twice.
+template <class K>
+inline cudaError_t ensure_dynamic_smem(K kernel, int bytes, std::atomic<unsigned long long> &done)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const bool tracked = dev >= 0 && dev < 64;
+    if (tracked && ((done.load(std::memory_order_acquire) >> dev) & 1ull)) return cudaSuccess;
+    if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+    if (tracked) done.fetch_or(1ull << dev, std::memory_order_release);
+    return cudaSuccess;
+}
 
 inline int status_from_cuda(cudaError_t e) { return e == cudaSuccess ? GEOM_OK : (int)e; }
 

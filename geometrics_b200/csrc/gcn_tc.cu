@@ -311,13 +311,8 @@ cudaError_t launch(int M, int K, int N, const float *X, const float *W, const fl
     const size_t smem = 2 * (2 * (size_t)kChunks * kAPlane + 2 * (size_t)kChunks * (g.Npad * 16 + 16));  // two buffers
     const size_t epi = 8 * 32 * 33 * sizeof(float);
     const size_t dyn = smem > epi ? smem : epi;
-    static bool attr_set[64] = {};  // per device: opt in to > 48 KB of dynamic shared memory once
-    int dev = 0;
-    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
-    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        if ((e = cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)) != cudaSuccess) return e;
-        if (dev >= 0 && dev < 64) attr_set[dev] = true;
-    }
+    static std::atomic<unsigned long long> smem_done{0};
+    if ((e = ensure_dynamic_smem(gemm_kernel, 110 * 1024, smem_done)) != cudaSuccess) return e;
     gemm_kernel<<<(unsigned)((M + 127) / 128), kThreads, dyn, st>>>(g);
     return cudaGetLastError();
 }

@@ -1,5 +1,30 @@
 // misc.cu -- version / status / device queries of the C ABI (include/geom_b200.h).
+#include <atomic>
+#include <cstring>
+
 #include "common.cuh"
+
+namespace geom {
+namespace debug {
+static std::atomic<unsigned> g_knob[GEOM_DEBUG_KNOBS];  // float bits; zero-initialised = not set
+float knob(int id)
+{
+    const unsigned u = g_knob[id].load(std::memory_order_relaxed);
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+}  // namespace debug
+}  // namespace geom
+
+extern "C" int geom_debug_set(int knob, float value)
+{
+    if (knob < 0 || knob >= GEOM_DEBUG_KNOBS) return GEOM_ERR_INVALID_ARG;
+    unsigned u;
+    memcpy(&u, &value, 4);
+    geom::debug::g_knob[knob].store(u, std::memory_order_relaxed);
+    return GEOM_OK;
+}
 
 extern "C" int geom_abi_version(void) { return GEOM_ABI_VERSION; }
 

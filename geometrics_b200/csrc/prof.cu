@@ -26,7 +26,9 @@ static const char *const kNames[kKernelCount] = {
     "geom::sample::sample_fwd_kernel", "geom::sample::sample_bwd_kernel", "geom::sample::area_kernel",
     "geom::gcn::gemm_kernel",       "geom::gcn::spmm_kernel",       "geom::gcn::bwd_kernel",
     "geom::tri::closest_kernel",    "geom::tri::closest_bwd_kernel", "geom::misc", "geom::misc2",
-    "geom::chamfer_tc::scan_kernel", "geom::chamfer_tc::pack_kernel", "geom::pool::fwd_kernel", "geom::pool::bwd_kernel"};
+    "geom::chamfer_tc::scan_kernel", "geom::chamfer_tc::pack_kernel", "geom::pool::fwd_kernel", "geom::pool::bwd_kernel",
+    "geom::tri_tc::scan_kernel", "geom::tri_tc::prep_kernel", "geom::gcn::bwd_gemm_kernel", "geom::bn::fwd_kernel",
+    "geom::bn::bwd_kernel", "geom::spare"};
 
 Scope::Scope(cudaStream_t st, int id) : st_(st), rec_(-1)
 {

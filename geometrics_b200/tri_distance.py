@@ -12,7 +12,9 @@ import torch
 from . import _lib
 
 
-def tri_forward(xyz1, tri1, tri2, tri3, *, exact_tail: bool = False, want_dist: bool = True):
+def tri_forward(xyz1, tri1, tri2, tri3, *, exact_tail: bool = False, want_dist: bool = True, tensor=None):
+    """``tensor``: None = the library picks (tensor-core filtered search from 2^24 pairs up), True / False force the
+    tensor-core filtered search / the CUDA-core brute force; the results are bit-identical."""
     _lib.require_cuda_f32("xyz1", xyz1, 3)
     for name, t in (("tri1", tri1), ("tri2", tri2), ("tri3", tri3)):
         _lib.require_cuda_f32(name, t, 3)
@@ -31,12 +33,20 @@ def tri_forward(xyz1, tri1, tri2, tri3, *, exact_tail: bool = False, want_dist: 
         dist = torch.empty((b, n), dtype=torch.float32, device=dev) if want_dist else None
         point = torch.empty((b, n), dtype=torch.int32, device=dev)
         index = torch.empty((b, n), dtype=torch.int32, device=dev)
-        ws_bytes = L.geom_tri_workspace_bytes(b, n)
-        ws = torch.empty(ws_bytes // 8 + 1, dtype=torch.int64, device=dev)
+        flags = _lib.GEOM_FLAG_EXACT_TAIL if exact_tail else 0
+        if tensor is None:
+            big = b * n * m >= (1 << 24)
+            ws_bytes = L.geom_tri_tensor_workspace_bytes(b, n, m) if big else L.geom_tri_workspace_bytes(b, n)
+        elif tensor:
+            flags |= _lib.GEOM_FLAG_TENSOR
+            ws_bytes = L.geom_tri_tensor_workspace_bytes(b, n, m)
+        else:
+            flags |= _lib.GEOM_FLAG_FP32
+            ws_bytes = L.geom_tri_workspace_bytes(b, n)
+        ws = torch.empty(ws_bytes // 8 + 1, dtype=torch.int64, device=dev)  # the caching allocator aligns to 512 bytes
         st = L.geom_tri_fwd(b, n, xyz1.data_ptr(), m, tri1.data_ptr(), tri2.data_ptr(), tri3.data_ptr(),
                             dist.data_ptr() if want_dist else None, point.data_ptr(), index.data_ptr(),
-                            ws.data_ptr(), ws.numel() * 8,
-                            _lib.GEOM_FLAG_EXACT_TAIL if exact_tail else 0, _lib.current_stream_ptr(dev))
+                            ws.data_ptr(), ws.numel() * 8, flags, _lib.current_stream_ptr(dev))
         _lib.check(st, "geom_tri_fwd")
     return dist, point, index
 

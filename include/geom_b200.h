@@ -7,8 +7,10 @@
  *   - all pointers are DEVICE pointers on the current CUDA device unless stated otherwise;
  *   - tensors are dense row-major fp32 / int32, exactly the layouts the reference passes
  *     (points (B,N,3); per-face vertices (B,F,3); indices (B,N));
- *   - the caller allocates every output and every workspace; nothing is retained across calls,
- *     there is no global state, calls are thread-safe;
+ *   - the caller allocates every output and every workspace; nothing is retained across calls and calls are
+ *     thread-safe.  Process-wide state is limited to: one atomic bit per (kernel, device) recording that the kernel
+ *     was opted in to > 48 KB of dynamic shared memory, and the debug knobs of geom_debug_set (tests / tuning only,
+ *     all zero = library defaults; nothing is read from the environment);
  *   - work is enqueued on `stream` (a cudaStream_t; 0 = legacy default stream, which is what the
  *     reference launchers use, chamfer_distance.cu:67-68 / tri_distance.cu:223) and the call
  *     returns without synchronising;
@@ -50,13 +52,13 @@ typedef void *geom_stream_t; /* cudaStream_t */
 #define GEOM_FLAG_EXACT_TAIL 1u
 /* Chamfer only: use the simple one-direction-at-a-time kernel instead of the fused two-way one. */
 #define GEOM_FLAG_ONEWAY 2u
-/* Chamfer only: tensor-core filtered exact search (tcgen05 bf16 contraction as a conservative filter,
+/* Chamfer and TriDistance: tensor-core filtered exact search (tcgen05 bf16 contraction as a conservative filter,
  * exact fp32 re-evaluation of the survivors); same results, bit for bit.  Needs a workspace of
  * geom_chamfer_tensor_workspace_bytes().  With neither GEOM_FLAG_TENSOR nor GEOM_FLAG_FP32 the library picks:
  * the tensor-core search when the workspace passed is large enough for it (and the sizes allow), the
  * CUDA-core search otherwise. */
 #define GEOM_FLAG_TENSOR 4u
-/* Chamfer only: force the CUDA-core (packed FP32) brute-force search. */
+/* Chamfer and TriDistance: force the CUDA-core brute-force search. */
 #define GEOM_FLAG_FP32 8u
 
 GEOM_API int geom_abi_version(void);
@@ -70,10 +72,22 @@ GEOM_API int geom_device_info(int *sm_count, int *cc_major, int *cc_minor);
  * the API is bracketed by CUDA events on its launch stream; geom_prof_end() synchronises on them and
  * returns, per kernel id, the summed device milliseconds and the launch count (arrays of
  * GEOM_PROF_KERNELS entries, either may be NULL).  Used by bench.py for the roofline figures. */
-#define GEOM_PROF_KERNELS 20
+#define GEOM_PROF_KERNELS 26
 GEOM_API int geom_prof_begin(void);
 GEOM_API int geom_prof_end(float *ms_per_kernel, int *launches_per_kernel);
 GEOM_API const char *geom_prof_kernel_name(int id);
+
+/* Debug knobs for tests and tuning sweeps (process-wide, atomic).  value 0 restores the library default.  Production
+ * callers never need them. */
+#define GEOM_DEBUG_TC_EPS_FACTOR 0      /* multiplies the Chamfer tensor-core filter margin (margin study) */
+#define GEOM_DEBUG_TRI_PR 1             /* CUDA-core TriDistance: points per lane (1, 2, 4) ... */
+#define GEOM_DEBUG_TRI_CHUNK 2          /* ... and triangles per work unit (64..512); both must be set */
+#define GEOM_DEBUG_TRI_TC_EPS_FACTOR 3  /* multiplies the TriDistance tensor-core filter margin */
+#define GEOM_DEBUG_CHAMFER_VARIANT 4    /* CUDA-core Chamfer: kernel variant + 1, */
+#define GEOM_DEBUG_CHAMFER_STRIP 5      /*   strip length, */
+#define GEOM_DEBUG_CHAMFER_TILE_COLS 6  /*   tile width */
+#define GEOM_DEBUG_KNOBS 8
+GEOM_API int geom_debug_set(int knob, float value);
 
 /* ---------------------------------------------------------------------------------------------
  * Chamfer nearest-neighbour search.
@@ -145,8 +159,14 @@ GEOM_API int geom_chamfer_loss_bwd(int b, int n, const float *xyz1, int m, const
  * index = face index.  Arithmetic and quirks (option-6 direction vector, NaN tile poisoning,
  * best=10000 initialisation) follow tri_distance.cu:124-206 as compiled; see DESIGN.md.
  * dist may be NULL.  workspace >= geom_tri_workspace_bytes(b, n), 8-byte aligned.
+ * Two interchangeable implementations return identical bits: the CUDA-core brute force (tri.cu) and the
+ * tensor-core filtered search (tri_tc.cu: a bf16 tcgen05 contraction over bounding spheres lower-bounds every
+ * (point, triangle) pair, only the pairs that can still win are evaluated with the reference arithmetic).  As for
+ * Chamfer: GEOM_FLAG_TENSOR / GEOM_FLAG_FP32 force one; with neither the filtered search runs when the workspace
+ * holds geom_tri_tensor_workspace_bytes(b, n, m) (16-byte aligned) and b*n*m >= 2^24.
  * ------------------------------------------------------------------------------------------- */
 GEOM_API size_t geom_tri_workspace_bytes(int b, int n);
+GEOM_API size_t geom_tri_tensor_workspace_bytes(int b, int n, int m);
 GEOM_API int geom_tri_fwd(int b, int n, const float *xyz, int m, const float *tri1, const float *tri2,
                  const float *tri3, float *dist, int *point, int *index,
                  void *workspace, size_t workspace_bytes, unsigned flags, geom_stream_t stream);

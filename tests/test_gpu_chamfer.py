@@ -224,14 +224,20 @@ def test_tensor_path_full_size_and_ranges(cuda, scale, offset):
             assert torch.equal(a_, b_) and torch.equal(c_, b_)
 
 
-def test_tensor_path_margin(cuda, monkeypatch):
+def test_tensor_path_margin(cuda):
     """The filter stays exact with its margin shrunk 8x: the shipped margin has headroom."""
     from geometrics_b200 import synth
     import geometrics_b200 as g
 
     x1, x2 = synth.random_points(8, 10000, 3).to(cuda), synth.random_points(8, 10000, 4).to(cuda)
     want = g.chamfer_forward(x1, x2, tensor=False)
-    monkeypatch.setenv("GEOM_TC_EPS_SCALE", "0.125")
-    got = g.chamfer_forward(x1, x2, tensor=True)
+    from geometrics_b200 import _lib
+
+    g.lib().geom_debug_set(_lib.GEOM_DEBUG_TC_EPS_FACTOR, 0.125)
+    try:
+        got = g.chamfer_forward(x1, x2, tensor=True)
+        torch.cuda.synchronize()
+    finally:
+        g.lib().geom_debug_set(_lib.GEOM_DEBUG_TC_EPS_FACTOR, 0.0)
     for a_, b_ in zip(got, want):
         assert torch.equal(a_, b_)

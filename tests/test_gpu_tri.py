@@ -20,25 +20,31 @@ def _cmp(got, want, what):
     assert (gp == wp).all(), f"{what}: {np.count_nonzero(gp != wp)} of {wp.size} options differ"
 
 
+@pytest.mark.parametrize("tensor", [False, True], ids=["cuda_cores", "tensor"])
 @pytest.mark.parametrize("exact", [False, True], ids=["default", "exact_tail"])
 @pytest.mark.parametrize("case", TRI_CASES, ids=_ids)
-def test_tri_matches_oracle(oracle, cuda, case, exact):
+def test_tri_matches_oracle(oracle, cuda, case, exact, tensor):
     import geometrics_b200 as g
 
     pts, t1, t2, t3 = tri_inputs(*case)
-    got = g.tri_forward(*(t.to(cuda) for t in (pts, t1, t2, t3)), exact_tail=exact)
+    if tensor and not exact and case[3] < 4:
+        pytest.skip("nothing is scanned for m < 4: the library always takes the plain path")
+    got = g.tri_forward(*(t.to(cuda) for t in (pts, t1, t2, t3)), exact_tail=exact, tensor=tensor)
     torch.cuda.synchronize()
     want = oracle.tri_fwd(pts.numpy(), t1.numpy(), t2.numpy(), t3.numpy(), exact=exact)
     _cmp(tuple(t.cpu().numpy() for t in got), want, str(case))
 
 
+@pytest.mark.parametrize("tensor", [False, True], ids=["cuda_cores", "tensor"])
 @pytest.mark.parametrize("case", TRI_CASES, ids=_ids)
-def test_tri_matches_reference_cuda(ref_cuda, cuda, case):
+def test_tri_matches_reference_cuda(ref_cuda, cuda, case, tensor):
     import geometrics_b200 as g
 
+    if tensor and case[3] < 4:
+        pytest.skip("nothing is scanned for m < 4: the library always takes the plain path")
     dev = tuple(t.to(cuda) for t in tri_inputs(*case))
     want = ref_cuda.tri_forward_t(*dev)
-    got = g.tri_forward(*dev)
+    got = g.tri_forward(*dev, tensor=tensor)
     torch.cuda.synchronize()
     _cmp(tuple(t.cpu().numpy() for t in got), tuple(t.cpu().numpy() for t in want), str(case))
 
@@ -53,19 +59,26 @@ def test_oracle_matches_reference_cuda(oracle, ref_cuda, cuda):
 
 
 @pytest.mark.parametrize("tune", ["1,64", "1,512", "2,128", "2,512", "4,256", "4,512"])
-def test_every_kernel_variant(oracle, cuda, tune, monkeypatch):
-    """Points-per-lane and chunk-size variants (normally picked from the problem size) all give the
-    reference's answer, on cases that exercise tile poisoning, the tail skip and multi-tile merges."""
+def test_every_kernel_variant(oracle, cuda, tune):
+    """Points-per-lane and chunk-size variants of the CUDA-core kernel (normally picked from the problem size) all
+    give the reference's answer, on cases that exercise tile poisoning, the tail skip and multi-tile merges."""
     import geometrics_b200 as g
+    from geometrics_b200 import _lib
 
-    monkeypatch.setenv("GEOM_TRI_TUNE", tune)
-    for case in [("degenerate0", 1, 200, 1100, 28), ("big", 1, 257, 2466, 30), ("onmesh", 2, 600, 960, 29),
-                 ("random", 2, 513, 1030, 23), ("random", 1, 300, 515, 24)]:
-        pts, t1, t2, t3 = tri_inputs(*case)
-        for exact in (False, True):
-            got = g.tri_forward(*(t.to(cuda) for t in (pts, t1, t2, t3)), exact_tail=exact)
-            want = oracle.tri_fwd(pts.numpy(), t1.numpy(), t2.numpy(), t3.numpy(), exact=exact)
-            _cmp(tuple(t.cpu().numpy() for t in got), want, f"{tune} {case} exact={exact}")
+    pr, chunk = (float(x) for x in tune.split(","))
+    g.lib().geom_debug_set(_lib.GEOM_DEBUG_TRI_PR, pr)
+    g.lib().geom_debug_set(_lib.GEOM_DEBUG_TRI_CHUNK, chunk)
+    try:
+        for case in [("degenerate0", 1, 200, 1100, 28), ("big", 1, 257, 2466, 30), ("onmesh", 2, 600, 960, 29),
+                     ("random", 2, 513, 1030, 23), ("random", 1, 300, 515, 24)]:
+            pts, t1, t2, t3 = tri_inputs(*case)
+            for exact in (False, True):
+                got = g.tri_forward(*(t.to(cuda) for t in (pts, t1, t2, t3)), exact_tail=exact, tensor=False)
+                want = oracle.tri_fwd(pts.numpy(), t1.numpy(), t2.numpy(), t3.numpy(), exact=exact)
+                _cmp(tuple(t.cpu().numpy() for t in got), want, f"{tune} {case} exact={exact}")
+    finally:
+        g.lib().geom_debug_set(_lib.GEOM_DEBUG_TRI_PR, 0.0)
+        g.lib().geom_debug_set(_lib.GEOM_DEBUG_TRI_CHUNK, 0.0)
 
 
 def test_module_surface(cuda):
@@ -106,7 +119,8 @@ def test_argument_errors(cuda):
     assert (d == 0).all() and (pt == 0).all() and (ix == 0).all()
 
 
-def test_full_size_config3(ref_cuda, cuda):
+@pytest.mark.parametrize("tensor", [False, True], ids=["cuda_cores", "tensor"])
+def test_full_size_config3(ref_cuda, cuda, tensor):
     """BASELINE config 3: 32 x (8192 points vs 5000 faces) on the jittered UV sphere."""
     from geometrics_b200 import synth
     import geometrics_b200 as g
@@ -114,14 +128,69 @@ def test_full_size_config3(ref_cuda, cuda):
     v, f = synth.uv_sphere(50, 50)
     t1, t2, t3 = (t.to(cuda) for t in synth.face_vertices(synth.mesh_batch(v, 32), f))
     pts = synth.random_points(32, 8192, 41).to(cuda)
-    got = g.tri_forward(pts, t1, t2, t3)
+    got = g.tri_forward(pts, t1, t2, t3, tensor=tensor)
     want = ref_cuda.tri_forward_t(pts, t1, t2, t3)
     for a, b in zip(got, want):
         assert torch.equal(a, b)
     # second stress set: independent random triangles
     r1, r2, r3 = (t.to(cuda) for t in synth.random_triangles(32, 5000))
-    got = g.tri_forward(pts, r1, r2, r3)
+    got = g.tri_forward(pts, r1, r2, r3, tensor=tensor)
     want = ref_cuda.tri_forward_t(pts, r1, r2, r3)
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+    # points near the surface (the training regime): shared-edge near-ties everywhere
+    vb = synth.mesh_batch(v, 32)
+    g_ = torch.Generator().manual_seed(7)
+    near = vb[:, torch.randint(0, vb.shape[1], (8192,), generator=g_)] * (1 + 0.02 * torch.randn(32, 8192, 1, generator=g_))
+    near = near.contiguous().to(cuda)
+    got = g.tri_forward(near, t1, t2, t3, tensor=tensor)
+    want = ref_cuda.tri_forward_t(near, t1, t2, t3)
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("scale,offset", [(1e-3, 0.0), (1.0, 50.0), (1e4, 0.0), (1e6, -3e6), (1e-12, 0.0), (1e16, 0.0)])
+def test_tensor_path_ranges(oracle, cuda, scale, offset):
+    """Coordinate ranges: the bf16 filter margin scales with R^2 (offsets make it useless but never wrong); magnitudes
+    it cannot handle (R <= 1e-15, R >= 1e15) take the in-kernel transcription of the reference loop."""
+    import geometrics_b200 as g
+
+    for case in [("sphere", 2, 700, 960, 31), ("random", 1, 300, 1030, 32), ("degenerate0", 1, 200, 1100, 33)]:
+        pts, t1, t2, t3 = (t * scale + offset for t in tri_inputs(*case))
+        got = g.tri_forward(*(t.to(cuda) for t in (pts, t1, t2, t3)), tensor=True)
+        want = oracle.tri_fwd(pts.numpy(), t1.numpy(), t2.numpy(), t3.numpy())
+        _cmp(tuple(t.cpu().numpy() for t in got), want, f"{case} x{scale}+{offset}")
+
+
+def test_tensor_path_nonfinite_points(oracle, cuda):
+    """NaN / Inf query points: the reference's first-candidate rule decides (tri_distance.cu:194,202)."""
+    import geometrics_b200 as g
+
+    pts, t1, t2, t3 = tri_inputs("sphere", 2, 600, 960, 34)
+    pts[0, 5, 1] = float("nan")
+    pts[1, 17, 0] = float("inf")
+    pts[1, 300] = float("-inf")
+    for tensor in (True, False):
+        got = g.tri_forward(*(t.to(cuda) for t in (pts, t1, t2, t3)), tensor=tensor)
+        want = oracle.tri_fwd(pts.numpy(), t1.numpy(), t2.numpy(), t3.numpy())
+        _cmp(tuple(t.cpu().numpy() for t in got), want, f"nonfinite tensor={tensor}")
+
+
+def test_tensor_path_margin(ref_cuda, cuda):
+    """The filter stays exact with its bf16 margin shrunk 8x: the shipped margin has headroom."""
+    from geometrics_b200 import synth, _lib
+    import geometrics_b200 as g
+
+    v, f = synth.uv_sphere(50, 50)
+    t1, t2, t3 = (t.to(cuda) for t in synth.face_vertices(synth.mesh_batch(v, 4), f))
+    pts = synth.random_points(4, 8192, 9).to(cuda)
+    want = ref_cuda.tri_forward_t(pts, t1, t2, t3)
+    g.lib().geom_debug_set(_lib.GEOM_DEBUG_TRI_TC_EPS_FACTOR, 0.125)
+    try:
+        got = g.tri_forward(pts, t1, t2, t3, tensor=True)
+        torch.cuda.synchronize()
+    finally:
+        g.lib().geom_debug_set(_lib.GEOM_DEBUG_TRI_TC_EPS_FACTOR, 0.0)
     for a, b in zip(got, want):
         assert torch.equal(a, b)
 

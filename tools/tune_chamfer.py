@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Sweep geom_chamfer_fwd kernel variants (GEOM_CHAMFER_TUNE="variant,strip,tile_cols") on the
-BASELINE config-2 workload; one subprocess per setting because the library reads the variable once.
+"""Sweep geom_chamfer_fwd CUDA-core kernel variants ("variant,strip,tile_cols", applied through the library's
+geom_debug_set knobs) on the BASELINE config-2 workload; one subprocess per setting.
 
     python tools/tune_chamfer.py [variant,strip,tile ...]      # parent: sweeps
 """
@@ -22,6 +22,13 @@ def child():
     B, N, M = 32, 10000, 10000
     sets = [(synth.random_points(B, N, 41 + i).to(dev), synth.random_points(B, M, 141 + i).to(dev)) for i in range(8)]
     L = g.lib()
+    tune = [int(x) for x in os.environ.get("_TUNE_SETTING", "").split(",") if x]
+    if len(tune) >= 1:
+        L.geom_debug_set(_lib.GEOM_DEBUG_CHAMFER_VARIANT, float(tune[0] + 1))
+    if len(tune) >= 2:
+        L.geom_debug_set(_lib.GEOM_DEBUG_CHAMFER_STRIP, float(tune[1]))
+    if len(tune) >= 3:
+        L.geom_debug_set(_lib.GEOM_DEBUG_CHAMFER_TILE_COLS, float(tune[2]))
     wsb = max(L.geom_chamfer_workspace_bytes(B, N, M), L.geom_chamfer_tensor_workspace_bytes(B, N, M))
     ws = torch.empty(wsb // 8 + 1, dtype=torch.int64, device=dev)
     i1 = torch.empty(B, N, dtype=torch.int32, device=dev)
@@ -57,7 +64,7 @@ def child():
     for k in range(K):
         step(k)
     kern = _lib.prof_end()
-    print(json.dumps({"tune": os.environ.get("GEOM_CHAMFER_TUNE", ""), "ok": ok, "step_ms": round(total, 4),
+    print(json.dumps({"tune": os.environ.get("_TUNE_SETTING", ""), "ok": ok, "step_ms": round(total, 4),
                       **{k.split("::")[-1]: round(v[0] / v[1], 4) for k, v in kern.items()}}), flush=True)
 
 
@@ -67,5 +74,5 @@ if __name__ == "__main__":
     else:
         settings = sys.argv[1:] or ["0,1", "0,2", "0,4", "1,2", "2,2", "3,2", "4,2", "0,2,128", "2,2,128", "4,2,128"]
         for s in settings:
-            env = dict(os.environ, _TUNE_CHILD="1", GEOM_CHAMFER_TUNE=s)
+            env = dict(os.environ, _TUNE_CHILD="1", _TUNE_SETTING=s)
             subprocess.run([sys.executable, os.path.abspath(__file__)], env=env, check=False)
