@@ -2,12 +2,15 @@
 """bench.py -- headline benchmark: Chamfer point-pairs/s on 32 x (10000 vs 10000) fp32 (BASELINE
 config 2), one process per GPU.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--scaling strong|weak]
 
 A "step" is one ChamferDistance nearest-neighbour search (both directions, the reference's
-ChamferDistanceKernelLauncher, chamfer_distance.cu:57-73) over one batch of 32 point-set pairs per
-GPU (weak scaling: the batch axis shards with no data-path collective).  point-pairs
-per step = B*n*m = 3.2e9 per GPU.
+ChamferDistanceKernelLauncher, chamfer_distance.cu:57-73) followed by the Chamfer loss sums on its
+indices (geom_chamfer_loss_fwd, utils.py:402-417) and, when the batch is sharded, ONE NCCL all-reduce of
+the two partial sums.  Default --scaling strong: the SAME 32 point-set pairs split
+32/16/8/4 per GPU at N = 1/2/4/8 (BASELINE metric: "32x10k vs 10k at 1/2/4/8 B200"); --scaling weak keeps
+32 per GPU.  point-pairs per step = global batch x n x m.  The all-reduce of step k is asynchronous: it
+overlaps the search of step k+1 and is waited for one step later, inside the timed region.
 
 Output: one JSON line (rank 0).  `value` = device-resident throughput (CUDA events, max over ranks);
 `e2e` = the same metric through the public API with pinned HOST buffers, H2D/D2H copies inside the
@@ -36,10 +39,14 @@ WORKLOAD = "ChamferDistance 32x(10000 vs 10000) fp32 NN search, both directions 
 RING = 24  # distinct input/output sets cycled through so the working set (24 x 15.4 MB) exceeds L2
 
 
-def _config(n_gpus):
-    return {"workload": WORKLOAD, "batch_per_gpu": B, "n": N_PTS, "m": M_PTS, "seed": SEED,
-            "global_batch": B * n_gpus, "parallelism": f"batch-sharded x{n_gpus}, no data-path collective",
-            "l2_policy": f"ring of {RING} distinct input/output/workspace sets (~370 MB > 126 MB L2), no reuse between consecutive steps"}
+def _config(n_gpus, scaling="strong"):
+    per_gpu = B // n_gpus if scaling == "strong" else B
+    return {"workload": WORKLOAD, "batch_per_gpu": per_gpu, "n": N_PTS, "m": M_PTS, "seed": SEED,
+            "global_batch": per_gpu * n_gpus,
+            "parallelism": f"batch axis sharded x{n_gpus} ({scaling} scaling), one all-reduce of the 2 loss sums per step"
+                           if n_gpus > 1 else "single GPU",
+            "step": "NN search (both directions) + Chamfer loss sums" + (" + NCCL all-reduce of the sums" if n_gpus > 1 else ""),
+            "l2_policy": f"ring of {RING} distinct input/output/workspace sets (> 126 MB L2 at N=1), no reuse between consecutive steps"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -135,8 +142,8 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": _config(args.gpus),
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": _config(args.gpus, args.scaling),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cb.threads, "kind": cb.kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -232,34 +239,83 @@ def run_product(args):
     stream = torch.cuda.current_stream(dev)
     sp = stream.cuda_stream
 
-    # ---- inputs: a ring of distinct sets (rank-dependent seeds), resident in HBM ----
+    # ---- inputs: a ring of distinct sets, resident in HBM.  strong scaling: rank r holds items [r*Bl, (r+1)*Bl) of the
+    #      same global batch of 32; weak: 32 items of its own per rank ----
+    strong = args.scaling == "strong"
+    if strong and B % world:
+        raise SystemExit(f"bench.py: --scaling strong needs a GPU count that divides the batch of {B}")
+    Bl = B // world if strong else B
     ring = []
     fp32_path = args.path == "fp32"
     flags = _lib.GEOM_FLAG_FP32 if fp32_path else 0
     # the tensor-core filtered search is the library's choice whenever the workspace is large enough for it
-    ws_bytes = (L.geom_chamfer_workspace_bytes if fp32_path else L.geom_chamfer_tensor_workspace_bytes)(B, N_PTS, M_PTS)
+    ws_bytes = (L.geom_chamfer_workspace_bytes if fp32_path else L.geom_chamfer_tensor_workspace_bytes)(Bl, N_PTS, M_PTS)
+    lws_bytes = L.geom_chamfer_loss_workspace_bytes(Bl, N_PTS, M_PTS)
     for r in range(RING):
-        x1, x2 = _host_inputs(SEED + 7 * r + 100000 * rank)
+        if strong:
+            x1, x2 = _host_inputs(SEED + 7 * r)
+            x1, x2 = x1[rank * Bl:(rank + 1) * Bl].contiguous(), x2[rank * Bl:(rank + 1) * Bl].contiguous()
+        else:
+            x1, x2 = _host_inputs(SEED + 7 * r + 100000 * rank)
         ring.append(dict(
             x1=x1.to(dev), x2=x2.to(dev),
-            i1=torch.empty(B, N_PTS, dtype=torch.int32, device=dev), i2=torch.empty(B, M_PTS, dtype=torch.int32, device=dev),
-            ws=torch.empty((ws_bytes + 15) // 16 * 2, dtype=torch.int64, device=dev)))
+            i1=torch.empty(Bl, N_PTS, dtype=torch.int32, device=dev), i2=torch.empty(Bl, M_PTS, dtype=torch.int32, device=dev),
+            ws=torch.empty((ws_bytes + 15) // 16 * 2, dtype=torch.int64, device=dev),
+            lws=torch.empty(max(lws_bytes // 16, 1) * 2, dtype=torch.float64, device=dev),
+            sums=torch.zeros(2, dtype=torch.float32, device=dev)))
 
-    def step(k):
-        s = ring[k % RING]
-        # indices only, as chamfer_distance.py:31 returns (dist pointers NULL)
-        st = L.geom_chamfer_fwd(B, N_PTS, s["x1"].data_ptr(), M_PTS, s["x2"].data_ptr(), None, s["i1"].data_ptr(),
-                                None, s["i2"].data_ptr(), s["ws"].data_ptr(), ws_bytes, flags, sp)
+    def step_kernels(s, sp_):
+        # indices only, as chamfer_distance.py:31 returns (dist pointers NULL); then the loss sums on them
+        st = L.geom_chamfer_fwd(Bl, N_PTS, s["x1"].data_ptr(), M_PTS, s["x2"].data_ptr(), None, s["i1"].data_ptr(),
+                                None, s["i2"].data_ptr(), s["ws"].data_ptr(), ws_bytes, flags, sp_)
         if st != 0:
             _lib.check(st, "geom_chamfer_fwd")
+        st = L.geom_chamfer_loss_fwd(Bl, N_PTS, s["x1"].data_ptr(), M_PTS, s["x2"].data_ptr(), s["i1"].data_ptr(),
+                                     s["i2"].data_ptr(), None, None, s["sums"].data_ptr(), s["lws"].data_ptr(),
+                                     s["lws"].numel() * 8, sp_)
+        if st != 0:
+            _lib.check(st, "geom_chamfer_loss_fwd")
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    # One CUDA graph per ring slot (search + loss: memsets, 2 pack launches, scan, 2 loss launches): at 4 items per GPU a
+    # step is ~100 us of device time, less than the host needs to launch it kernel by kernel.
+    graphs = None
+    if not args.no_graph:
+        for k in range(2):
+            step_kernels(ring[k], sp)  # first-use work (shared-memory opt-in) must happen outside a capture
+        torch.cuda.synchronize(dev)
+        graphs = []
+        for s in ring:
+            gph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gph):
+                step_kernels(s, torch.cuda.current_stream(dev).cuda_stream)
+            graphs.append(gph)
+
+    pending = []
+
+    def step(k):
+        if graphs is not None:
+            graphs[k % RING].replay()
+        else:
+            step_kernels(ring[k % RING], sp)
+        if world > 1:
+            # the ONE collective of the path: all-reduce of the two partial loss sums, asynchronous -- it overlaps the
+            # next step's search and is waited for (stream-side) one step later
+            pending.append(dist.all_reduce(ring[k % RING]["sums"], async_op=True))
+            if len(pending) > 1:
+                pending.pop(0).wait()
+
+    def drain():
+        while pending:
+            pending.pop(0).wait()
+
     for k in range(args.warmup):
         step(k)
+    drain()
     barrier()
     sampler = ClockSampler(_physical_gpu_index(local))
     sampler.start()
@@ -267,16 +323,32 @@ def run_product(args):
     e0.record(stream)
     for k in range(args.steps):
         step(args.warmup + k)
+    drain()
     e1.record(stream)
     barrier()
     ms_total = e0.elapsed_time(e1)
     clocks = sampler.stop()
 
-    # ---- second pass of the same K steps with the library's per-kernel event timing on: average
-    #      launch duration of each kernel over the timed region, on the launch stream ----
+    # ---- the same step for >= 2 s: what the rate settles at once the part is under sustained load ----
+    sustained = None
+    if args.sustain_s > 0:
+        n_sus = max(args.steps, int(args.sustain_s * 1e3 / max(ms_total / args.steps, 1e-3)) + 1)
+        sam2 = ClockSampler(_physical_gpu_index(local))
+        sam2.start()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        for k in range(n_sus):
+            step(k)
+        drain()
+        s1.record(stream)
+        barrier()
+        sustained = {"steps": n_sus, "ms_total": s0.elapsed_time(s1), "clocks": sam2.stop()}
+
+    # ---- second pass of the same K steps with the library's per-kernel event timing on (direct launches, no graph):
+    #      average launch duration of each kernel, on the launch stream ----
     _lib.prof_begin()
     for k in range(args.steps):
-        step(args.warmup + k)
+        step_kernels(ring[(args.warmup + k) % RING], sp)
     kern = _lib.prof_end()  # {name: (total ms, launches)}
     barrier()
     dom_name = max(kern, key=lambda k_: kern[k_][0])
@@ -284,10 +356,14 @@ def run_product(args):
     launches = sum(c for _, c in kern.values())
 
     # ---- end to end: pinned host buffers in, indices out, copies inside the timed region ----
-    hx1, hx2 = _host_inputs(SEED + 100000 * rank)
+    if strong:
+        hx1, hx2 = _host_inputs(SEED)
+        hx1, hx2 = hx1[rank * Bl:(rank + 1) * Bl].contiguous(), hx2[rank * Bl:(rank + 1) * Bl].contiguous()
+    else:
+        hx1, hx2 = _host_inputs(SEED + 100000 * rank)
     hx1, hx2 = hx1.pin_memory(), hx2.pin_memory()
-    hi1 = torch.empty(B, N_PTS, dtype=torch.int32).pin_memory()
-    hi2 = torch.empty(B, M_PTS, dtype=torch.int32).pin_memory()
+    hi1 = torch.empty(Bl, N_PTS, dtype=torch.int32).pin_memory()
+    hi2 = torch.empty(Bl, M_PTS, dtype=torch.int32).pin_memory()
     e2e_steps = max(3, min(args.steps, 30))
     for _ in range(2):
         g.chamfer_forward_host(hx1, hx2, hi1, hi2, device=dev, chunks=args.e2e_chunks, tensor=False if fp32_path else None)
@@ -300,12 +376,12 @@ def run_product(args):
     e2e_s = (time.perf_counter() - t0) / e2e_steps
 
     # ---- reduce over ranks (max time) ----
-    t = torch.tensor([ms_total, e2e_s, kern_ms or 0.0], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, e2e_s, kern_ms or 0.0, sustained["ms_total"] if sustained else 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_s, kern_ms_max = (float(v) for v in t.tolist())
+    ms_total, e2e_s, kern_ms_max, sus_ms = (float(v) for v in t.tolist())
     ms_step = ms_total / args.steps
-    pairs_step = B * N_PTS * M_PTS * world
+    pairs_step = Bl * N_PTS * M_PTS * world
 
     if rank == 0:
         peaks = {}
@@ -320,7 +396,8 @@ def run_product(args):
             traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
         except Exception:
             pass
-        alg_bytes = 16 * B * (N_PTS + M_PTS)  # read 12 B/point, write one int32 index/point
+        B_ = Bl  # the dominant kernel's launch covers this rank's shard
+        alg_bytes = 16 * B_ * (N_PTS + M_PTS)  # read 12 B/point, write one int32 index/point
         dom_ms = kern_ms_max
         ach = alg_bytes / (dom_ms * 1e-3) / 1e9
         sm_mhz = clocks.get("sm_mhz") or 1965
@@ -330,39 +407,44 @@ def run_product(args):
             # tensor-core filtered search: one M128 N64 K16 bf16 MMA per (128 query rows x 64 candidates), both
             # directions, over the padded extents (rows to 512, candidates to 128); minima on the ALU pipe
             pad = lambda v, q: (v + q - 1) // q * q
-            mma_flops = 2 * 16 * B * (pad(N_PTS, 512) * pad(M_PTS, 128) + pad(M_PTS, 512) * pad(N_PTS, 128))
+            mma_flops = 2 * 16 * B_ * (pad(N_PTS, 512) * pad(M_PTS, 128) + pad(M_PTS, 512) * pad(N_PTS, 128))
             tc_peak = float(peaks.get("bf16_tflops", 1650.0))
             tc_ach = mma_flops / (dom_ms * 1e-3) / 1e12
             alu_peak = 148 * 64 * sm_mhz * 1e6    # ALU pipe: 16 lanes x 4 SMSP per SM
-            alu_ops = B * N_PTS * M_PTS           # 3-input minimum: one lane-op per two approximate distances, two directions
-            roofline = {"bound": "tensor", "achieved": tc_ach, "peak": tc_peak, "unit": "TFLOP/s", "frac": tc_ach / tc_peak,
+            alu_ops = B_ * N_PTS * M_PTS          # 3-input minimum: one lane-op per two approximate distances, two directions
+            alg_flops = 16 * B_ * N_PTS * M_PTS  # 8 flop per distance evaluation, 2*B*n*m evaluations
+            alg_ach = alg_flops / (dom_ms * 1e-3) / 1e12
+            # `achieved` / `frac` follow SURVEY.md 8d's ALGORITHMIC flops; the flops the tensor core actually issues (K padded
+            # 3 -> 16 for the 15-term bf16 split, extents padded to 512 / 128) are reported beside them as issued_*
+            roofline = {"bound": "tensor", "achieved": alg_ach, "peak": tc_peak, "unit": "TFLOP/s", "frac": alg_ach / tc_peak,
+                        "issued_tflops": tc_ach, "issued_frac": tc_ach / tc_peak,
                         "traffic": traffic, "traffic_source": traffic_src,
                         "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1650 TFLOP/s",
-                        "kernel": dom_name, "kernel_ms": dom_ms, "flops_per_launch": mma_flops,
-                        # SURVEY.md 8d's algorithmic figure: 8 flop per distance evaluation, 2*B*n*m evaluations
-                        "algorithmic_flops_per_launch": 16 * B * N_PTS * M_PTS,
-                        "algorithmic_tflops": 16 * B * N_PTS * M_PTS / (dom_ms * 1e-3) / 1e12,
-                        "note": "flops = issued tcgen05.mma shapes (K=16 carries the 15-term split distance); the kernel is "
-                                "bound by the TMEM accumulator round trip and the ALU-pipe minima, not by HBM (see DESIGN.md 4.1)",
+                        "kernel": dom_name, "kernel_ms": dom_ms, "issued_flops_per_launch": mma_flops,
+                        "algorithmic_flops_per_launch": alg_flops,
+                        "note": "achieved = SURVEY 8d algorithmic flops (8 per distance evaluation) / kernel time; issued_* = the "
+                                "tcgen05.mma shapes actually launched (K=16 carries the 15-term split distance); the kernel is bound "
+                                "by the TMEM accumulator round trip and the ALU-pipe minima, not by HBM (see DESIGN.md 4.1)",
                         "hbm": hbm,
                         "alu": {"lane_ops_per_launch": alu_ops, "achieved_tlops": alu_ops / (dom_ms * 1e-3) / 1e12,
                                 "peak_tlops": alu_peak / 1e12, "frac": alu_ops / (dom_ms * 1e-3) / alu_peak,
                                 "peak_source": f"148 SM x 64 ALU lanes x {sm_mhz} MHz (median SM clock during the run)"}}
         else:
             fp32_peak = 148 * 128 * sm_mhz * 1e6  # FP32 lane-ops/s at the clock observed under load
-            lane_ops = 6 * B * N_PTS * M_PTS      # 3 sub + 1 mul + 2 fma per pair, each pair evaluated once
+            lane_ops = 6 * B_ * N_PTS * M_PTS     # 3 sub + 1 mul + 2 fma per pair, each pair evaluated once
             roofline = dict(hbm, bound="hbm", traffic=traffic, traffic_source=traffic_src, kernel=dom_name, kernel_ms=dom_ms,
                             note="brute-force NN is FP32-issue bound, not HBM bound (SURVEY.md 8d); see fp32 below",
                             fp32={"lane_ops_per_launch": lane_ops, "achieved_tlops": lane_ops / (dom_ms * 1e-3) / 1e12,
                                   "peak_tlops": fp32_peak / 1e12, "frac": lane_ops / (dom_ms * 1e-3) / fp32_peak,
                                   "peak_source": f"148 SM x 128 FP32 lanes x {sm_mhz} MHz (median SM clock during the run)"})
-        cfg = _config(world)
-        cfg["search_path"] = "CUDA-core packed-FP32 brute force (GEOM_FLAG_FP32)" if fp32_path else \
+        cfg = _config(world, args.scaling)
+        search_path = "CUDA-core packed-FP32 brute force (GEOM_FLAG_FP32)" if fp32_path else \
             "tensor-core filtered exact search (tcgen05 bf16 filter + exact fp32 re-evaluation; library default)"
         out = {
             "metric": METRIC, "value": pairs_step / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+            "search_path": search_path, "launch": "direct" if graphs is None else "CUDA graph per step (search + loss), NCCL all-reduce outside the graph",
             "clocks": clocks,
             "e2e": {"value": pairs_step / e2e_s, "unit": UNIT, "h2d_bytes_per_step": hx1.numel() * 4 + hx2.numel() * 4,
                     "d2h_bytes_per_step": hi1.numel() * 4 + hi2.numel() * 4, "ms_per_step": e2e_s * 1e3,
@@ -372,6 +454,11 @@ def run_product(args):
                         for k_, v in kern.items()},
             "roofline": roofline,
         }
+        if traffic is not None:
+            out["roofline"]["traffic_note"] = "DRAM bytes per launch from the committed ncu --set full capture named in traffic_source (a constant of that capture, not measured in this run)"
+        if sustained:
+            out["sustained"] = {"value": pairs_step / (sus_ms / sustained["steps"] * 1e-3), "unit": UNIT, "steps": sustained["steps"],
+                                "seconds": sus_ms * 1e-3, "ms_per_step": sus_ms / sustained["steps"], "clocks": sustained["clocks"]}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_block()
         sys.stdout.flush()
@@ -389,6 +476,10 @@ def main():
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-chunks", type=int, default=5, help="batch chunks pipelined by geom_chamfer_fwd_host")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: the same 32 items split over the GPUs (BASELINE metric); weak: 32 items per GPU")
+    ap.add_argument("--no-graph", action="store_true", help="launch kernel by kernel instead of one CUDA graph per step")
+    ap.add_argument("--sustain-s", type=float, default=2.0, help="also time the step for at least this many seconds (0 = skip)")
     ap.add_argument("--path", default="auto", choices=["auto", "fp32"], help="auto = library default (tensor-core filtered search); fp32 = CUDA-core brute force")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "product" else args.warmup

@@ -27,6 +27,7 @@ GEOM_DEBUG_TRI_TC_EPS_FACTOR = 3
 GEOM_DEBUG_CHAMFER_VARIANT = 4
 GEOM_DEBUG_CHAMFER_STRIP = 5
 GEOM_DEBUG_CHAMFER_TILE_COLS = 6
+GEOM_DEBUG_TC_CHUNKS = 7
 
 # every symbol include/geom_b200.h declares: name -> (restype, argtypes)
 _vp, _i, _u, _sz = C.c_void_p, C.c_int, C.c_uint, C.c_size_t

@@ -400,7 +400,7 @@ constexpr int kOneWayTile = 512;
 __global__ void __launch_bounds__(kOneWayThreads)
 oneway_kernel(const float *__restrict__ qpts, int q_full, int q0, int nq,
               const float *__restrict__ cpts, int c_full, int mc,
-              float *__restrict__ dist, int *__restrict__ idx, int zero_if_pos)
+              float *__restrict__ dist, int *__restrict__ idx, int zero_if_pos, int flat)
 {
     __shared__ __align__(16) float sx[kOneWayTile], sy[kOneWayTile], sz[kOneWayTile];
     const int bi = blockIdx.y;
@@ -415,11 +415,17 @@ oneway_kernel(const float *__restrict__ qpts, int q_full, int q0, int nq,
         qx[r] = q[rr * 3 + 0];
         qy[r] = q[rr * 3 + 1];
         qz[r] = q[rr * 3 + 2];
-        best[r] = __int_as_float(0x7f800000);
+        best[r] = 0.f;
         besti[r] = 0;
     }
+    // The reference's control flow, so that NaN / Inf inputs get the reference's answers: the first candidate of every
+    // 512-tile is taken unconditionally (chamfer_distance.cu:39), tiles merge with a strict '>' (:47).  flat
+    // (GEOM_FLAG_EXACT_TAIL): one tile spanning every candidate.
+    float tb[kOneWayQR];
+    int tbi[kOneWayQR];
     for (int k0 = 0; k0 < mc; k0 += kOneWayTile) {
         const int tk = min(kOneWayTile, mc - k0);
+        const bool tile_start = !flat || k0 == 0;
         __syncthreads();
         for (int e = threadIdx.x; e < tk * 3; e += kOneWayThreads) {
             const int pt = e / 3, cc = e - pt * 3;
@@ -433,11 +439,19 @@ oneway_kernel(const float *__restrict__ qpts, int q_full, int q0, int nq,
 #pragma unroll
             for (int r = 0; r < kOneWayQR; ++r) {
                 const float d = sqdist_ref(qx[r], qy[r], qz[r], cx, cy, cz);
-                if (d < best[r]) {
-                    best[r] = d;
-                    besti[r] = k0 + k;
+                if ((k == 0 && tile_start) || d < tb[r]) {
+                    tb[r] = d;
+                    tbi[r] = k0 + k;
                 }
             }
+        }
+        if (!flat || k0 + kOneWayTile >= mc) {
+#pragma unroll
+            for (int r = 0; r < kOneWayQR; ++r)
+                if ((flat ? true : k0 == 0) || best[r] > tb[r]) {
+                    best[r] = tb[r];
+                    besti[r] = tbi[r];
+                }
         }
     }
 #pragma unroll
@@ -455,15 +469,48 @@ oneway_kernel(const float *__restrict__ qpts, int q_full, int q0, int nq,
     }
 }
 
+// Two-way path only: its key merges assume ordered (non-NaN) distances.  One pass flags non-finite coordinates ...
+__global__ void __launch_bounds__(256) finite_check_kernel(const float *__restrict__ a, long long na, const float *__restrict__ b_, long long nb,
+                                                           unsigned *__restrict__ flag)
+{
+    const long long stride = (long long)gridDim.x * 256;
+    float acc = 0.f;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < na + nb; i += stride) acc += (i < na ? a[i] : b_[i - na]) * 0.0f;
+    if (__syncthreads_or(acc != 0.0f || acc != acc)) {  // x * 0 is NaN exactly for NaN / Inf
+        if (threadIdx.x == 0) atomicExch(flag, 1u);
+    }
+}
+// ... and when the flag is set every row is redone with the reference's own control flow (a no-op launch otherwise).
+__global__ void __launch_bounds__(256)
+nonfinite_fixup_kernel(const unsigned *__restrict__ flag, int b, int n, const float *__restrict__ xyz1, int m, const float *__restrict__ xyz2,
+                       float *dist1, int *idx1, float *dist2, int *idx2, int exact)
+{
+    if (*flag == 0u) return;
+    const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (t >= (long long)b * (n + m)) return;
+    const bool second = t >= (long long)b * n;
+    const long long u = second ? t - (long long)b * n : t;
+    const int nq = second ? m : n, nc = second ? n : m;
+    const int bi = (int)(u / nq);
+    const float *q = (second ? xyz2 : xyz1) + (size_t)u * 3;
+    const float *c = (second ? xyz1 : xyz2) + (size_t)bi * nc * 3;
+    float res;
+    int res_i;
+    chamfer_ref_row(q[0], q[1], q[2], c, nc, exact != 0, res, res_i);
+    float *dist = second ? dist2 : dist1;
+    if (dist) dist[u] = res;
+    (second ? idx2 : idx1)[u] = res_i;
+}
+
 static cudaError_t launch_oneway(int b, const float *q, int q_full, int q0, int nq, const float *c,
-                                 int c_full, int mc, float *dist, int *idx, int zero, cudaStream_t st)
+                                 int c_full, int mc, float *dist, int *idx, int zero, int flat, cudaStream_t st)
 {
     if (nq <= 0 || b <= 0) return cudaSuccess;
     const int per_cta = kOneWayThreads * kOneWayQR;
     dim3 grid((nq + per_cta - 1) / per_cta, b);
     {
         prof::Scope ps(st, prof::kChamferOneWay);
-        oneway_kernel<<<grid, kOneWayThreads, 0, st>>>(q, q_full, q0, nq, c, c_full, mc, dist, idx, zero);
+        oneway_kernel<<<grid, kOneWayThreads, 0, st>>>(q, q_full, q0, nq, c, c_full, mc, dist, idx, zero, flat);
     }
     return cudaGetLastError();
 }
@@ -542,8 +589,8 @@ extern "C" int geom_chamfer_fwd(int b, int n, const float *xyz1, int m, const fl
     const bool tc_fits = workspace && workspace_bytes >= tc_need && !((uintptr_t)workspace & 15u);
     if (tc_possible && ((flags & GEOM_FLAG_TENSOR) || tc_fits)) {
         if (!tc_fits) return GEOM_ERR_WORKSPACE;
-        return status_from_cuda(chamfer_tc::launch(b, n, xyz1, m, xyz2, n_scan, m_scan, zero1, zero2, dist1, idx1, dist2,
-                                                   idx2, workspace, st));
+        return status_from_cuda(chamfer_tc::launch(b, n, xyz1, m, xyz2, n_scan, m_scan, zero1, zero2, exact ? 1 : 0, dist1,
+                                                   idx1, dist2, idx2, workspace, st));
     }
     const bool twoway = !(flags & GEOM_FLAG_ONEWAY) && n_scan > 0 && m_scan > 0;
     if (twoway) {
@@ -635,20 +682,29 @@ extern "C" int geom_chamfer_fwd(int b, int n, const float *xyz1, int m, const fl
         if ((e = cudaGetLastError()) != cudaSuccess) return status_from_cuda(e);
 
         // queries beyond the trimmed extents still need an answer over the trimmed candidates
-        if ((e = launch_oneway(b, xyz1, n, n_scan, n - n_scan, xyz2, m, m_scan, dist1, idx1, zero1, st)) != cudaSuccess)
+        if ((e = launch_oneway(b, xyz1, n, n_scan, n - n_scan, xyz2, m, m_scan, dist1, idx1, zero1, exact ? 1 : 0, st)) != cudaSuccess)
             return status_from_cuda(e);
-        if ((e = launch_oneway(b, xyz2, m, m_scan, m - m_scan, xyz1, n, n_scan, dist2, idx2, zero2, st)) != cudaSuccess)
+        if ((e = launch_oneway(b, xyz2, m, m_scan, m - m_scan, xyz1, n, n_scan, dist2, idx2, zero2, exact ? 1 : 0, st)) != cudaSuccess)
             return status_from_cuda(e);
-        return GEOM_OK;
+        {
+            // NaN / Inf inputs: detect, then redo with the reference's control flow (both launches are ~free when finite)
+            unsigned *flag = a.ticket + 2;
+            if ((e = cudaMemsetAsync(flag, 0, 4, st)) != cudaSuccess) return status_from_cuda(e);
+            prof::Scope ps(st, prof::kMisc2);
+            finite_check_kernel<<<sms * 4, 256, 0, st>>>(xyz1, (long long)b * n * 3, xyz2, (long long)b * m * 3, flag);
+            nonfinite_fixup_kernel<<<(unsigned)(((long long)b * (n + m) + 255) / 256), 256, 0, st>>>(flag, b, n, xyz1, m, xyz2, dist1, idx1,
+                                                                                                  dist2, idx2, exact ? 1 : 0);
+        }
+        return status_from_cuda(cudaGetLastError());
     }
 
     if (n > 0) {
-        e = (m_scan > 0) ? launch_oneway(b, xyz1, n, 0, n, xyz2, m, m_scan, dist1, idx1, zero1, st)
+        e = (m_scan > 0) ? launch_oneway(b, xyz1, n, 0, n, xyz2, m, m_scan, dist1, idx1, zero1, exact ? 1 : 0, st)
                          : fill_zero(b, n, dist1, idx1, st);
         if (e != cudaSuccess) return status_from_cuda(e);
     }
     if (m > 0) {
-        e = (n_scan > 0) ? launch_oneway(b, xyz2, m, 0, m, xyz1, n, n_scan, dist2, idx2, zero2, st)
+        e = (n_scan > 0) ? launch_oneway(b, xyz2, m, 0, m, xyz1, n, n_scan, dist2, idx2, zero2, exact ? 1 : 0, st)
                          : fill_zero(b, m, dist2, idx2, st);
         if (e != cudaSuccess) return status_from_cuda(e);
     }

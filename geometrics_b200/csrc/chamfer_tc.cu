@@ -108,11 +108,15 @@ struct SearchArgs {
     int *idx;             // (b, nq)
     int nq, nq_pad, nc, nc_full, nc_pad;  // nc = scanned candidates (tail-trimmed), nc_full = array stride
     int zero_if_pos;      // reference "empty final tile" behaviour (chamfer_distance.cu:29-30,47)
+    u64 *keys;            // (b, nq) merge keys (distance bits << 32 | index), 0xff..: only when the candidates are split
+    unsigned *done;       // (b, nq_pad / 512) arrival counters of the row blocks, 0: only when the candidates are split
 };
 struct SearchArgs2 {
     SearchArgs dir[2];    // blockIdx.z selects the direction
     const unsigned *rmax_bits;
     float eps_scale;      // kEpsScale (tests shrink it to measure the safety margin)
+    int exact;            // GEOM_FLAG_EXACT_TAIL (only the non-finite slow path needs to know)
+    int chunks;           // CTAs per row block, each sweeping 1/chunks of the candidate tiles (small batches: fills the GPU)
 };
 
 struct ScanSmem {
@@ -125,6 +129,7 @@ struct ScanSmem {
     unsigned long long b_full[kStages], b_free[kStages];             // ring stage landed / no longer read
     unsigned long long a_full;
     unsigned tmem_slot;
+    unsigned last_flag;   // candidate split: this CTA is the last of its row block to arrive
 };
 
 __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 both)
@@ -134,10 +139,14 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 bot
     const SearchArgs &a = both.dir[blockIdx.z];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int bi = blockIdx.y;
-    const int row0 = blockIdx.x * kRowsPerCta;
+    const int rblock = (int)blockIdx.x / both.chunks, chunk = (int)blockIdx.x % both.chunks;
+    const int row0 = rblock * kRowsPerCta;
     if (row0 >= a.nq_pad) return;  // the grid covers the longer of the two directions
-    const int ntiles = (a.nc + kTileCols - 1) / kTileCols;
-    const uint4 *gB = a.formB + (size_t)bi * a.nc_pad * 2;
+    // this CTA sweeps candidate tiles [tile0, tile0 + ntiles) of the direction's tiles
+    const int all_tiles = (a.nc + kTileCols - 1) / kTileCols;
+    const int tile0 = (int)((long long)all_tiles * chunk / both.chunks);
+    const int ntiles = (int)((long long)all_tiles * (chunk + 1) / both.chunks) - tile0;
+    const uint4 *gB = a.formB + ((size_t)bi * a.nc_pad + (size_t)tile0 * kTileCols) * 2;
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_slot)), "r"((unsigned)kTmemCols));
@@ -309,18 +318,44 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 bot
             const float tm = fminf(fminf(bm0, bm1), fminf(bm2, bm3));
             if (!(tm > mt + eps2)) {  // predicated append: the tile holds a candidate inside the window
                 evm[(size_t)cnt * kScanThreads] = make_uint4(__float_as_uint(bm0), __float_as_uint(bm1), __float_as_uint(bm2), __float_as_uint(bm3));
-                evt[(size_t)cnt * kScanThreads] = (unsigned)t;
+                evt[(size_t)cnt * kScanThreads] = (unsigned)(tile0 + t);
                 ++cnt;
             }
             if (cnt >= kEvCap) flush();
         }
         flush();
-        if (valid) {
+        const size_t off = (size_t)bi * a.nq + qrow;
+        bool write = valid;
+        if (!(rmax < __int_as_float(0x7f800000))) {
+            // Some input coordinate is NaN / Inf: the reference's answer depends on WHERE it sits in the 512-tiles
+            // (chamfer_distance.cu:39,47), so every row is redone by the transcription of the reference loop.
+            write = false;
+            if (valid && chunk == 0) {
+                chamfer_ref_row(qx, qy, qz, cb, a.nc_full, both.exact != 0, best, bidx);
+                if (a.dist) a.dist[off] = best;
+                a.idx[off] = bidx;
+            }
+        } else if (both.chunks > 1) {
+            // The row block's candidates are split over several CTAs: results meet in 64-bit keys (smaller distance, then
+            // lower index = the reference's tie rule); the CTA that arrives last decodes them.
+            if (valid) atomicMin(&a.keys[off], make_key(best, (unsigned)bidx));
+            __threadfence();
+            asm volatile("bar.sync 1, %0;" ::"n"(kScanThreads) : "memory");
+            if (tid == 0) S.last_flag = atomicAdd(&a.done[(size_t)bi * (a.nq_pad / kRowsPerCta) + rblock], 1u) == (unsigned)both.chunks - 1u;
+            asm volatile("bar.sync 1, %0;" ::"n"(kScanThreads) : "memory");
+            write = valid && S.last_flag;
+            if (write) {
+                __threadfence();
+                const u64 k = *(volatile u64 *)&a.keys[off];
+                best = __uint_as_float((unsigned)(k >> 32));
+                bidx = (int)(unsigned)k;
+            }
+        }
+        if (write) {
             if (a.zero_if_pos && best > 0.0f) {
                 best = 0.0f;
                 bidx = 0;
             }
-            const size_t off = (size_t)bi * a.nq + qrow;
             if (a.dist) a.dist[off] = best;
             a.idx[off] = bidx;
         }
@@ -335,7 +370,27 @@ static size_t pad_rows(int cnt) { return ((size_t)cnt + kRowsPerCta - 1) / kRows
 size_t workspace_bytes(int b, int n, int m)
 {
     // four packed arrays (A and B form of both sets, 32 B per padded row each) + the R scalar
-    return ((size_t)b * (pad_rows(n) + pad_rows(m)) * 2) * 32 + 256;
+    // + merge keys (8 B per padded row) and row-block arrival counters for the candidate split of small batches
+    const size_t rows = (size_t)b * (pad_rows(n) + pad_rows(m));
+    return rows * 2 * 32 + 256 + rows * 8 + (rows / kRowsPerCta) * 4 + 256;
+}
+
+// CTAs per row block: split the candidate sweep when whole row blocks would leave SMs idle or the last wave nearly
+// empty.  Cost model in tile-steps: waves x (tiles per CTA + ~5 tiles of prologue, pipeline fill and final flush).
+static int pick_chunks(long long row_blocks, int tiles, int sms)
+{
+    int best_c = 1;
+    double best_cost = 1e30;
+    for (int c = 1; c <= 8; ++c) {
+        if (c > 1 && tiles / c < 8) break;
+        const double waves = (double)((row_blocks * c + sms - 1) / sms);
+        const double cost = waves * ((double)tiles / c + 5.0);
+        if (cost < best_cost * 0.97) {  // prefer fewer chunks unless the gain is real: every chunk re-evaluates its own winners
+            best_cost = cost;
+            best_c = c;
+        }
+    }
+    return best_c;
 }
 
 int ctas_per_item(int n, int m)
@@ -347,7 +402,7 @@ int ctas_per_item(int n, int m)
 // Both directions.  n_scan / m_scan: candidates actually scanned (reference tail skip); zero1 / zero2: the
 // reference's empty-final-tile behaviour.  Requires n_scan > 0 and m_scan > 0.
 cudaError_t launch(int b, int n, const float *xyz1, int m, const float *xyz2, int n_scan, int m_scan, int zero1,
-                   int zero2, float *dist1, int *idx1, float *dist2, int *idx2, void *workspace, cudaStream_t st)
+                   int zero2, int exact, float *dist1, int *idx1, float *dist2, int *idx2, void *workspace, cudaStream_t st)
 {
     const size_t np = pad_rows(n), mp = pad_rows(m);
     char *w = (char *)workspace;
@@ -367,6 +422,7 @@ cudaError_t launch(int b, int n, const float *xyz1, int m, const float *xyz2, in
     SearchArgs2 s;
     s.rmax_bits = rmax;
     s.eps_scale = kEpsScale;
+    s.exact = exact;
     if (const float f = debug::knob(GEOM_DEBUG_TC_EPS_FACTOR); f > 0.f) s.eps_scale = kEpsScale * f;  // tests: margin study
     // direction 0: every xyz1 point over xyz2[0, m_scan);  direction 1: every xyz2 point over xyz1[0, n_scan)
     SearchArgs &d0 = s.dir[0], &d1 = s.dir[1];
@@ -375,11 +431,31 @@ cudaError_t launch(int b, int n, const float *xyz1, int m, const float *xyz2, in
     d1.qxyz = xyz2, d1.cxyz = xyz1, d1.formA = a2, d1.formB = b1, d1.dist = dist2, d1.idx = idx2;
     d1.nq = m, d1.nq_pad = (int)mp, d1.nc = n_scan, d1.nc_full = n, d1.nc_pad = (int)np, d1.zero_if_pos = zero2;
     {
+        int dev = 0, sms = 148;
+        if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+        if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+        const int tiles = (int)(((n_scan > m_scan ? n_scan : m_scan) + kTileCols - 1) / kTileCols);
+        s.chunks = pick_chunks((long long)b * ((np + mp) / kRowsPerCta), tiles, sms);
+        if (const float f = debug::knob(GEOM_DEBUG_TC_CHUNKS); f >= 1.f && f <= 8.f) s.chunks = (int)f;  // tests
+        d0.keys = d1.keys = nullptr;
+        d0.done = d1.done = nullptr;
+        if (s.chunks > 1) {
+            char *kbase = (char *)(b2 + (size_t)b * mp * 2);  // behind the packed operands (16-byte aligned)
+            const size_t key_bytes = (size_t)b * (np + mp) * 8, cnt_bytes = (size_t)b * ((np + mp) / kRowsPerCta) * 4;
+            d0.keys = (u64 *)kbase;
+            d1.keys = d0.keys + (size_t)b * n;
+            d0.done = (unsigned *)(kbase + key_bytes);
+            d1.done = d0.done + (size_t)b * (np / kRowsPerCta);
+            if ((e = cudaMemsetAsync(kbase, 0xff, key_bytes, st)) != cudaSuccess) return e;
+            if ((e = cudaMemsetAsync(kbase + key_bytes, 0, cnt_bytes, st)) != cudaSuccess) return e;
+        }
+    }
+    {
         prof::Scope ps(st, prof::kChamferTcScan);
         const size_t rows = np > mp ? np : mp;
         static std::atomic<unsigned long long> smem_done{0};
         if ((e = ensure_dynamic_smem(scan_kernel, (int)sizeof(ScanSmem), smem_done)) != cudaSuccess) return e;
-        scan_kernel<<<dim3((unsigned)(rows / kRowsPerCta), b, 2), kThreads, sizeof(ScanSmem), st>>>(s);
+        scan_kernel<<<dim3((unsigned)(rows / kRowsPerCta) * s.chunks, b, 2), kThreads, sizeof(ScanSmem), st>>>(s);
     }
     return cudaGetLastError();
 }

@@ -98,6 +98,36 @@ __device__ __forceinline__ float sqdist_ref(float qx, float qy, float qz, float 
     return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
 }
 
+// One query against candidates c[0, nc_full) with the reference kernel's own control flow (chamfer_distance.cu:18-54):
+// 512-candidate tiles, the first candidate of a tile taken unconditionally (:39), strict '<' inside a tile, strict '>'
+// across tiles (:47), the last (tile length mod 4) candidates never examined (:31-33) -- the slow path that gives
+// NaN / Inf inputs exactly what the reference gives them.  exact (GEOM_FLAG_EXACT_TAIL): one flat tile, nothing skipped.
+__device__ inline void chamfer_ref_row(float qx, float qy, float qz, const float *__restrict__ c, int nc_full, bool exact,
+                                       float &res, int &res_i)
+{
+    res = 0.f;
+    res_i = 0;
+    const int step = exact ? (nc_full > 0 ? nc_full : 1) : 512;
+    for (int k2 = 0; k2 < nc_full; k2 += step) {
+        const int end_k = (nc_full < k2 + step ? nc_full : k2 + step) - k2;
+        const int end_ka = exact ? end_k : end_k - (end_k & 3);
+        float best = 0.f;
+        int best_i = 0;
+        for (int k = 0; k < end_ka; ++k) {
+            const float *p = c + (size_t)(k2 + k) * 3;
+            const float d = sqdist_ref(qx, qy, qz, __ldg(p), __ldg(p + 1), __ldg(p + 2));
+            if (k == 0 || d < best) {
+                best = d;
+                best_i = k + k2;
+            }
+        }
+        if (k2 == 0 || res > best) {
+            res = best;
+            res_i = best_i;
+        }
+    }
+}
+
 // (distance bits << 32) | tag.  Distances are >= +0, so their bit patterns order like the values and
 // an unsigned 64-bit min picks the smallest distance, then the smallest tag.
 __device__ __forceinline__ u64 make_key(float d, unsigned tag)
@@ -135,7 +165,7 @@ namespace chamfer_tc {
 size_t workspace_bytes(int b, int n, int m);
 int ctas_per_item(int n, int m);  // thread blocks one batch item contributes to the search grid (one CTA per SM)
 cudaError_t launch(int b, int n, const float *xyz1, int m, const float *xyz2, int n_scan, int m_scan, int zero1,
-                   int zero2, float *dist1, int *idx1, float *dist2, int *idx2, void *workspace, cudaStream_t st);
+                   int zero2, int exact, float *dist1, int *idx1, float *dist2, int *idx2, void *workspace, cudaStream_t st);
 }  // namespace chamfer_tc
 
 // tensor-core filtered point-to-triangle search (tri_tc.cu)

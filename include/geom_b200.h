@@ -86,6 +86,7 @@ GEOM_API const char *geom_prof_kernel_name(int id);
 #define GEOM_DEBUG_CHAMFER_VARIANT 4    /* CUDA-core Chamfer: kernel variant + 1, */
 #define GEOM_DEBUG_CHAMFER_STRIP 5      /*   strip length, */
 #define GEOM_DEBUG_CHAMFER_TILE_COLS 6  /*   tile width */
+#define GEOM_DEBUG_TC_CHUNKS 7          /* Chamfer tensor-core search: CTAs per row block (1..8; candidate split) */
 #define GEOM_DEBUG_KNOBS 8
 GEOM_API int geom_debug_set(int knob, float value);
 

@@ -241,3 +241,82 @@ def test_tensor_path_margin(cuda):
         g.lib().geom_debug_set(_lib.GEOM_DEBUG_TC_EPS_FACTOR, 0.0)
     for a_, b_ in zip(got, want):
         assert torch.equal(a_, b_)
+
+
+@pytest.mark.parametrize("chunks", [2, 3, 4, 8])
+def test_tensor_path_candidate_split(oracle, cuda, chunks):
+    """Small batches split every row block's candidate sweep over several CTAs (results meet in 64-bit keys, the last
+    CTA to arrive decodes): same bits as the oracle, tail semantics and lattice / duplicate ties included."""
+    import geometrics_b200 as g
+    from geometrics_b200 import _lib
+
+    g.lib().geom_debug_set(_lib.GEOM_DEBUG_TC_CHUNKS, float(chunks))
+    try:
+        for case in [("random", 2, 2466, 3000, 6), ("random", 1, 300, 10001, 8), ("lattice", 2, 4100, 4099, 11),
+                     ("dup", 2, 3000, 2466, 13), ("random", 2, 1500, 999, 7), ("cluster", 2, 1640, 1300, 15)]:
+            x1, x2 = chamfer_inputs(*case)
+            for exact in (False, True):
+                got = _run(x1, x2, cuda, tensor=True, exact_tail=exact)
+                want = oracle.chamfer_fwd(x1.numpy(), x2.numpy(), exact=exact)
+                for name, g_, w_ in zip(("dist1", "idx1", "dist2", "idx2"), got, want):
+                    if name.startswith("dist"):
+                        assert_same_f32(g_, w_, f"{case} {name}")
+                    else:
+                        assert (g_ == w_).all(), f"{case} {name}: {np.count_nonzero(g_ != w_)} of {w_.size} indices differ"
+    finally:
+        g.lib().geom_debug_set(_lib.GEOM_DEBUG_TC_CHUNKS, 0.0)
+
+
+@pytest.mark.parametrize("b", [1, 4, 8])
+def test_tensor_path_small_batches_full_size(cuda, b):
+    """The per-GPU batches of the strong-scaling split (32 items over 4 / 8 GPUs) at full size: the library's own choice
+    of the candidate split must match the CUDA-core kernel bit for bit."""
+    from geometrics_b200 import synth
+    import geometrics_b200 as g
+
+    x1, x2 = synth.random_points(b, 10000, 51).to(cuda), synth.random_points(b, 10000, 52).to(cuda)
+    want = g.chamfer_forward(x1, x2, tensor=False)
+    got = g.chamfer_forward(x1, x2)
+    for a_, b_ in zip(got, want):
+        assert torch.equal(a_, b_)
+
+
+@pytest.mark.parametrize("mode", [dict(), dict(tensor=False), dict(oneway=True), dict(tensor=True, exact_tail=True),
+                                  dict(tensor=False, exact_tail=True)],
+                         ids=["tensor", "cuda_cores", "oneway", "tensor_exact", "cuda_cores_exact"])
+def test_nonfinite_inputs_follow_the_reference(oracle, cuda, mode):
+    """NaN / Inf coordinates: the reference takes the first candidate of every 512-tile unconditionally
+    (chamfer_distance.cu:39) and merges tiles with a strict '>' (:47), so a NaN distance at a tile start voids that tile
+    and a NaN at tile 0 sticks.  Every path reproduces the oracle (= the reference kernel restated) bit for bit."""
+    x1, x2 = chamfer_inputs("random", 2, 1300, 1538, 91)
+    x2[0, 0, 1] = float("nan")        # candidate 0 of tile 0
+    x2[0, 512, 0] = float("inf")      # first candidate of tile 1
+    x2[1, 700] = float("nan")         # mid-tile: simply never the minimum
+    x2[1, 1024, 2] = float("-inf")    # first candidate of tile 2
+    x1[0, 3, 0] = float("nan")        # NaN query
+    x1[1, 77] = float("inf")          # Inf query
+    x1[1, 512, 1] = float("nan")      # also a tile start of the other direction
+    got = _run(x1, x2, cuda, **mode)
+    want = oracle.chamfer_fwd(x1.numpy(), x2.numpy(), exact=bool(mode.get("exact_tail")))
+    for name, g_, w_ in zip(("dist1", "idx1", "dist2", "idx2"), got, want):
+        if name.startswith("dist"):
+            assert_same_f32(g_, w_, name)
+        else:
+            assert (g_ == w_).all(), f"{name}: {np.count_nonzero(g_ != w_)} of {w_.size} indices differ"
+
+
+def test_nonfinite_inputs_match_reference_cuda(ref_cuda, cuda):
+    import geometrics_b200 as g
+
+    x1, x2 = chamfer_inputs("random", 2, 1030, 2466, 92)
+    x2[0, 0] = float("nan")
+    x2[1, 512, 2] = float("nan")
+    x1[0, 9, 1] = float("inf")
+    x1d, x2d = x1.to(cuda), x2.to(cuda)
+    want = ref_cuda.chamfer_forward_t(x1d, x2d)
+    for kw in (dict(), dict(tensor=False), dict(oneway=True)):
+        got = g.chamfer_forward(x1d, x2d, **kw)
+        torch.cuda.synchronize()
+        for a_, b_ in zip(got, want):
+            assert_same_f32(a_.cpu().numpy().view(np.float32) if a_.dtype == torch.float32 else a_.cpu().numpy().astype(np.float32),
+                            b_.cpu().numpy().view(np.float32) if b_.dtype == torch.float32 else b_.cpu().numpy().astype(np.float32), str(kw))
