@@ -10,7 +10,7 @@ indices (geom_chamfer_loss_fwd, utils.py:402-417) and, when the batch is sharded
 the two partial sums.  Default --scaling strong: the SAME 32 point-set pairs split
 32/16/8/4 per GPU at N = 1/2/4/8 (BASELINE metric: "32x10k vs 10k at 1/2/4/8 B200"); --scaling weak keeps
 32 per GPU.  point-pairs per step = global batch x n x m.  The all-reduce of step k is asynchronous: it
-overlaps the search of step k+1 and is waited for one step later, inside the timed region.
+overlaps the searches of steps k+1, k+2 and is waited for two steps later, inside the timed region.
 
 Output: one JSON line (rank 0).  `value` = device-resident throughput (CUDA events, max over ranks);
 `e2e` = the same metric through the public API with pinned HOST buffers, H2D/D2H copies inside the
@@ -213,9 +213,22 @@ def _physical_gpu_index(local_rank):
 # ------------------------------------------------------------------------------------------------
 # product arm
 # ------------------------------------------------------------------------------------------------
+def _note(msg):
+    """Progress lines on stderr (stdout carries exactly one JSON line): a stuck multi-GPU run shows where it stopped."""
+    sys.stderr.write(f"[bench rank {os.environ.get('RANK', '0')} +{time.perf_counter() - _T0:7.2f}s] {msg}\n")
+    sys.stderr.flush()
+
+
+_T0 = time.perf_counter()
+
+
 def run_product(args):
+    import faulthandler
+
     import torch
     import torch.distributed as dist
+
+    faulthandler.dump_traceback_later(args.watchdog_s, exit=True)  # a hung collective must not eat the GPU lease
 
     import geometrics_b200 as g
     from geometrics_b200 import _lib
@@ -232,15 +245,14 @@ def run_product(args):
     sys.stdout.flush()
     saved_stdout = os.dup(1)
     os.dup2(2, 1)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
     L = g.lib()
     stream = torch.cuda.current_stream(dev)
     sp = stream.cuda_stream
 
     # ---- inputs: a ring of distinct sets, resident in HBM.  strong scaling: rank r holds items [r*Bl, (r+1)*Bl) of the
     #      same global batch of 32; weak: 32 items of its own per rank ----
+    global B
+    B = args.global_batch
     strong = args.scaling == "strong"
     if strong and B % world:
         raise SystemExit(f"bench.py: --scaling strong needs a GPU count that divides the batch of {B}")
@@ -283,6 +295,7 @@ def run_product(args):
 
     # One CUDA graph per ring slot (search + loss: memsets, 2 pack launches, scan, 2 loss launches): at 4 items per GPU a
     # step is ~100 us of device time, less than the host needs to launch it kernel by kernel.
+    _note(f"inputs resident: {RING} sets of {Bl} items per rank")
     graphs = None
     if not args.no_graph:
         for k in range(2):
@@ -295,6 +308,14 @@ def run_product(args):
                 step_kernels(s, torch.cuda.current_stream(dev).cuda_stream)
             graphs.append(gph)
 
+    # NCCL comes up only now: graph capture and a live NCCL watchdog thread do not mix (a capture in progress forbids
+    # the event queries the watchdog issues from its own thread)
+    _note("graphs captured" if graphs is not None else "direct launches")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        _note("NCCL process group up")
+
     pending = []
 
     def step(k):
@@ -304,9 +325,10 @@ def run_product(args):
             step_kernels(ring[k % RING], sp)
         if world > 1:
             # the ONE collective of the path: all-reduce of the two partial loss sums, asynchronous -- it overlaps the
-            # next step's search and is waited for (stream-side) one step later
+            # following searches and is waited for (stream-side) two steps later: its kernel needs an SM on every GPU
+            # at about the same time, and the search keeps all of them busy until a wave of CTAs retires
             pending.append(dist.all_reduce(ring[k % RING]["sums"], async_op=True))
-            if len(pending) > 1:
+            if len(pending) > 2:
                 pending.pop(0).wait()
 
     def drain():
@@ -317,22 +339,30 @@ def run_product(args):
         step(k)
     drain()
     barrier()
+    _note("warm-up done")
     sampler = ClockSampler(_physical_gpu_index(local))
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
+    h0 = time.perf_counter()
     for k in range(args.steps):
         step(args.warmup + k)
+    host_us = (time.perf_counter() - h0) / args.steps * 1e6  # host time to enqueue one step
     drain()
     e1.record(stream)
     barrier()
     ms_total = e0.elapsed_time(e1)
     clocks = sampler.stop()
+    _note(f"timed region done: {ms_total / args.steps:.4f} ms/step")
 
     # ---- the same step for >= 2 s: what the rate settles at once the part is under sustained load ----
     sustained = None
     if args.sustain_s > 0:
         n_sus = max(args.steps, int(args.sustain_s * 1e3 / max(ms_total / args.steps, 1e-3)) + 1)
+        if world > 1:  # every rank must run the SAME number of steps (each step carries a collective): rank 0 decides
+            nt = torch.tensor([n_sus], dtype=torch.int64, device=dev)
+            dist.broadcast(nt, 0)
+            n_sus = int(nt.item())
         sam2 = ClockSampler(_physical_gpu_index(local))
         sam2.start()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -343,6 +373,7 @@ def run_product(args):
         s1.record(stream)
         barrier()
         sustained = {"steps": n_sus, "ms_total": s0.elapsed_time(s1), "clocks": sam2.stop()}
+        _note("sustained region done")
 
     # ---- second pass of the same K steps with the library's per-kernel event timing on (direct launches, no graph):
     #      average launch duration of each kernel, on the launch stream ----
@@ -354,6 +385,7 @@ def run_product(args):
     dom_name = max(kern, key=lambda k_: kern[k_][0])
     kern_ms = kern[dom_name][0] / kern[dom_name][1]
     launches = sum(c for _, c in kern.values())
+    _note("per-kernel pass done")
 
     # ---- end to end: pinned host buffers in, indices out, copies inside the timed region ----
     if strong:
@@ -374,6 +406,7 @@ def run_product(args):
         g.chamfer_forward_host(hx1, hx2, hi1, hi2, device=dev, chunks=args.e2e_chunks, tensor=False if fp32_path else None)
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
+    _note("end-to-end pass done")
 
     # ---- reduce over ranks (max time) ----
     t = torch.tensor([ms_total, e2e_s, kern_ms or 0.0, sustained["ms_total"] if sustained else 0.0], dtype=torch.float64, device=dev)
@@ -445,7 +478,7 @@ def run_product(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
             "search_path": search_path, "launch": "direct" if graphs is None else "CUDA graph per step (search + loss), NCCL all-reduce outside the graph",
-            "clocks": clocks,
+            "clocks": clocks, "host_enqueue_us_per_step": host_us,
             "e2e": {"value": pairs_step / e2e_s, "unit": UNIT, "h2d_bytes_per_step": hx1.numel() * 4 + hx2.numel() * 4,
                     "d2h_bytes_per_step": hi1.numel() * 4 + hi2.numel() * 4, "ms_per_step": e2e_s * 1e3,
                     "api": "geom_chamfer_fwd_host via geometrics_b200.chamfer_forward_host (pinned host in/out, batch chunks pipelined)", "chunks": args.e2e_chunks, "steps": e2e_steps},
@@ -480,6 +513,8 @@ def main():
                     help="strong: the same 32 items split over the GPUs (BASELINE metric); weak: 32 items per GPU")
     ap.add_argument("--no-graph", action="store_true", help="launch kernel by kernel instead of one CUDA graph per step")
     ap.add_argument("--sustain-s", type=float, default=2.0, help="also time the step for at least this many seconds (0 = skip)")
+    ap.add_argument("--global-batch", type=int, default=B, help="items in the global batch (the BASELINE config is 32)")
+    ap.add_argument("--watchdog-s", type=float, default=240.0, help="dump every thread's stack and exit if the run takes longer")
     ap.add_argument("--path", default="auto", choices=["auto", "fp32"], help="auto = library default (tensor-core filtered search); fp32 = CUDA-core brute force")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "product" else args.warmup

@@ -116,7 +116,12 @@ struct SearchArgs2 {
     const unsigned *rmax_bits;
     float eps_scale;      // kEpsScale (tests shrink it to measure the safety margin)
     int exact;            // GEOM_FLAG_EXACT_TAIL (only the non-finite slow path needs to know)
-    int chunks;           // CTAs per row block, each sweeping 1/chunks of the candidate tiles (small batches: fills the GPU)
+    // Grid layout (1-D).  Row blocks (512 query rows of one batch item and direction) are numbered direction 0 first;
+    // the first n_whole of them get ONE CTA each that sweeps every candidate tile; each of the others gets `chunks` CTAs
+    // that sweep 1/chunks of the tiles and merge through 64-bit keys -- the remainder that would otherwise run as a nearly
+    // empty last wave (small batches) is spread over the whole GPU instead.
+    int b, blocks0, blocks1;  // row blocks per item of direction 0 / 1
+    int n_whole, chunks;
 };
 
 struct ScanSmem {
@@ -132,20 +137,36 @@ struct ScanSmem {
     unsigned last_flag;   // candidate split: this CTA is the last of its row block to arrive
 };
 
+// blockIdx.x -> (direction, batch item, row block, candidate chunk, chunks of this row block); see SearchArgs2
+__device__ __forceinline__ void decode_cta(const SearchArgs2 &both, int &dirsel, int &bi, int &rblock, int &chunk, int &nchunks)
+{
+    int rb_lin = (int)blockIdx.x;
+    chunk = 0, nchunks = 1;
+    if (rb_lin >= both.n_whole) {
+        const int j = rb_lin - both.n_whole;
+        rb_lin = both.n_whole + j / both.chunks;
+        chunk = j % both.chunks;
+        nchunks = both.chunks;
+    }
+    dirsel = rb_lin >= both.b * both.blocks0 ? 1 : 0;
+    const int per_item = dirsel ? both.blocks1 : both.blocks0;
+    const int rb_dir = rb_lin - (dirsel ? both.b * both.blocks0 : 0);
+    bi = rb_dir / per_item, rblock = rb_dir % per_item;
+}
+
 __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 both)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     ScanSmem &S = *reinterpret_cast<ScanSmem *>(smem_raw);
-    const SearchArgs &a = both.dir[blockIdx.z];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int bi = blockIdx.y;
-    const int rblock = (int)blockIdx.x / both.chunks, chunk = (int)blockIdx.x % both.chunks;
+    int dirsel, bi, rblock, chunk, nchunks;
+    decode_cta(both, dirsel, bi, rblock, chunk, nchunks);
+    const SearchArgs &a = both.dir[dirsel];
     const int row0 = rblock * kRowsPerCta;
-    if (row0 >= a.nq_pad) return;  // the grid covers the longer of the two directions
     // this CTA sweeps candidate tiles [tile0, tile0 + ntiles) of the direction's tiles
     const int all_tiles = (a.nc + kTileCols - 1) / kTileCols;
-    const int tile0 = (int)((long long)all_tiles * chunk / both.chunks);
-    const int ntiles = (int)((long long)all_tiles * (chunk + 1) / both.chunks) - tile0;
+    const int tile0 = (int)((long long)all_tiles * chunk / nchunks);
+    const int ntiles = (int)((long long)all_tiles * (chunk + 1) / nchunks) - tile0;
     const uint4 *gB = a.formB + ((size_t)bi * a.nc_pad + (size_t)tile0 * kTileCols) * 2;
 
     if (warp == 0) {
@@ -229,7 +250,9 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 bot
         const float rmax = __uint_as_float(*both.rmax_bits);
         // |dt - d| <= eps; inputs too large for the bf16 split to stay finite disable the filter (eps = inf)
         const float eps2 = (rmax < 1.0e15f) ? 2.0f * both.eps_scale * rmax * rmax : __int_as_float(0x7f800000);
-        const float *cb = a.cxyz + (size_t)bi * a.nc_full * 3;
+        // candidate indices are local to this CTA's tile range inside the sweep (tile0 is added back at the end)
+        const float *cb = a.cxyz + ((size_t)bi * a.nc_full + (size_t)tile0 * kTileCols) * 3;
+        const int nc_loc = a.nc - tile0 * kTileCols, nc_full_loc = a.nc_full - tile0 * kTileCols;
         const bool vec_ok = (((uintptr_t)cb) & 15u) == 0;
         uint4 *evm = &S.evm[0][tid];
         unsigned *evt = &S.evt[0][tid];
@@ -260,12 +283,12 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 bot
                 const int j0 = (int)blk[((size_t)(e >> 2) * kScanThreads + tid) * 4 + (e & 3)] * 32;
                 auto cand = [&](int j, float cx, float cy, float cz) {
                     const float d = sqdist_ref(qx, qy, qz, cx, cy, cz);
-                    if (j < a.nc && d < best) {  // ascending j + strict '<': lowest index among exact ties
+                    if (j < nc_loc && d < best) {  // ascending j + strict '<': lowest index among exact ties
                         best = d;
                         bidx = j;
                     }
                 };
-                if (vec_ok && j0 + 32 <= a.nc_full) {
+                if (vec_ok && j0 + 32 <= nc_full_loc) {
                     const float4 *p = reinterpret_cast<const float4 *>(cb + (size_t)j0 * 3);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
@@ -276,7 +299,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 bot
                         cand(j0 + 4 * i + 3, u2.y, u2.z, u2.w);
                     }
                 } else {
-                    const int jend = min(j0 + 32, a.nc);
+                    const int jend = min(j0 + 32, nc_loc);
                     for (int j = j0; j < jend; ++j) cand(j, __ldg(cb + (size_t)j * 3), __ldg(cb + (size_t)j * 3 + 1), __ldg(cb + (size_t)j * 3 + 2));
                 }
             }
@@ -318,7 +341,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 bot
             const float tm = fminf(fminf(bm0, bm1), fminf(bm2, bm3));
             if (!(tm > mt + eps2)) {  // predicated append: the tile holds a candidate inside the window
                 evm[(size_t)cnt * kScanThreads] = make_uint4(__float_as_uint(bm0), __float_as_uint(bm1), __float_as_uint(bm2), __float_as_uint(bm3));
-                evt[(size_t)cnt * kScanThreads] = (unsigned)(tile0 + t);
+                evt[(size_t)cnt * kScanThreads] = (unsigned)t;
                 ++cnt;
             }
             if (cnt >= kEvCap) flush();
@@ -326,22 +349,25 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 bot
         flush();
         const size_t off = (size_t)bi * a.nq + qrow;
         bool write = valid;
+        int dirsel_, bi_, rblock, chunk, nchunks;  // recomputed: nothing of the grid decode stays live through the sweep
+        decode_cta(both, dirsel_, bi_, rblock, chunk, nchunks);
+        bidx += (int)((long long)((a.nc + kTileCols - 1) / kTileCols) * chunk / nchunks) * kTileCols;
         if (!(rmax < __int_as_float(0x7f800000))) {
             // Some input coordinate is NaN / Inf: the reference's answer depends on WHERE it sits in the 512-tiles
             // (chamfer_distance.cu:39,47), so every row is redone by the transcription of the reference loop.
             write = false;
             if (valid && chunk == 0) {
-                chamfer_ref_row(qx, qy, qz, cb, a.nc_full, both.exact != 0, best, bidx);
+                chamfer_ref_row(qx, qy, qz, a.cxyz + (size_t)bi * a.nc_full * 3, a.nc_full, both.exact != 0, best, bidx);
                 if (a.dist) a.dist[off] = best;
                 a.idx[off] = bidx;
             }
-        } else if (both.chunks > 1) {
+        } else if (nchunks > 1) {
             // The row block's candidates are split over several CTAs: results meet in 64-bit keys (smaller distance, then
             // lower index = the reference's tie rule); the CTA that arrives last decodes them.
             if (valid) atomicMin(&a.keys[off], make_key(best, (unsigned)bidx));
             __threadfence();
             asm volatile("bar.sync 1, %0;" ::"n"(kScanThreads) : "memory");
-            if (tid == 0) S.last_flag = atomicAdd(&a.done[(size_t)bi * (a.nq_pad / kRowsPerCta) + rblock], 1u) == (unsigned)both.chunks - 1u;
+            if (tid == 0) S.last_flag = atomicAdd(&a.done[(size_t)bi * (a.nq_pad / kRowsPerCta) + rblock], 1u) == (unsigned)nchunks - 1u;
             asm volatile("bar.sync 1, %0;" ::"n"(kScanThreads) : "memory");
             write = valid && S.last_flag;
             if (write) {
@@ -375,28 +401,34 @@ size_t workspace_bytes(int b, int n, int m)
     return rows * 2 * 32 + 256 + rows * 8 + (rows / kRowsPerCta) * 4 + 256;
 }
 
-// CTAs per row block: split the candidate sweep when whole row blocks would leave SMs idle or the last wave nearly
-// empty.  Cost model in tile-steps: waves x (tiles per CTA + ~5 tiles of prologue, pipeline fill and final flush).
-static int pick_chunks(long long row_blocks, int tiles, int sms)
+// Grid plan: row blocks that fill whole waves of the one-CTA-per-SM grid sweep all their candidate tiles; the remaining
+// row blocks are split `chunks` ways so that the last wave covers the GPU too.  Costs in tile-steps, fitted on B200
+// (profiles/r02_tc_chunks.txt): a CTA costs its tiles + ~16 tiles of prologue, pipeline fill, final flush and key merge.
+static void plan_grid(long long row_blocks, int tiles, int sms, int &n_whole, int &chunks)
 {
-    int best_c = 1;
-    double best_cost = 1e30;
-    for (int c = 1; c <= 8; ++c) {
-        if (c > 1 && tiles / c < 8) break;
-        const double waves = (double)((row_blocks * c + sms - 1) / sms);
-        const double cost = waves * ((double)tiles / c + 5.0);
-        if (cost < best_cost * 0.97) {  // prefer fewer chunks unless the gain is real: every chunk re-evaluates its own winners
-            best_cost = cost;
-            best_c = c;
+    const double kCtaOverhead = 16.0;
+    const long long rem = row_blocks % sms;
+    n_whole = (int)row_blocks;
+    chunks = 1;
+    if (rem == 0 || row_blocks > 0x3fffffffLL / 8) return;
+    const double whole_cost = (double)tiles + kCtaOverhead;  // the remainder as one more wave of whole sweeps
+    double best = whole_cost;
+    for (int c = 2; c <= 8; ++c) {
+        if (tiles / c < 8) break;
+        const double waves = (double)((rem * c + sms - 1) / sms);
+        const double cost = waves * ((double)tiles / c + kCtaOverhead);
+        if (cost < best * 0.97) {
+            best = cost;
+            chunks = c;
         }
     }
-    return best_c;
+    if (chunks > 1) n_whole = (int)(row_blocks - rem);
 }
 
 int ctas_per_item(int n, int m)
 {
     const size_t np = pad_rows(n), mp = pad_rows(m);
-    return (int)(2 * ((np > mp ? np : mp) / kRowsPerCta));
+    return (int)((np + mp) / kRowsPerCta);
 }
 
 // Both directions.  n_scan / m_scan: candidates actually scanned (reference tail skip); zero1 / zero2: the
@@ -435,8 +467,16 @@ cudaError_t launch(int b, int n, const float *xyz1, int m, const float *xyz2, in
         if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
         if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
         const int tiles = (int)(((n_scan > m_scan ? n_scan : m_scan) + kTileCols - 1) / kTileCols);
-        s.chunks = pick_chunks((long long)b * ((np + mp) / kRowsPerCta), tiles, sms);
-        if (const float f = debug::knob(GEOM_DEBUG_TC_CHUNKS); f >= 1.f && f <= 8.f) s.chunks = (int)f;  // tests
+        s.b = b;
+        s.blocks0 = (int)(np / kRowsPerCta);
+        s.blocks1 = (int)(mp / kRowsPerCta);
+        const long long row_blocks = (long long)b * (s.blocks0 + s.blocks1);
+        if (row_blocks > 0x3fffffffLL / 8) return cudaErrorInvalidValue;
+        plan_grid(row_blocks, tiles, sms, s.n_whole, s.chunks);
+        if (const float f = debug::knob(GEOM_DEBUG_TC_CHUNKS); f >= 1.f && f <= 8.f) {  // tests: split EVERY row block
+            s.chunks = (int)f;
+            s.n_whole = s.chunks > 1 ? 0 : (int)row_blocks;
+        }
         d0.keys = d1.keys = nullptr;
         d0.done = d1.done = nullptr;
         if (s.chunks > 1) {
@@ -452,10 +492,11 @@ cudaError_t launch(int b, int n, const float *xyz1, int m, const float *xyz2, in
     }
     {
         prof::Scope ps(st, prof::kChamferTcScan);
-        const size_t rows = np > mp ? np : mp;
         static std::atomic<unsigned long long> smem_done{0};
         if ((e = ensure_dynamic_smem(scan_kernel, (int)sizeof(ScanSmem), smem_done)) != cudaSuccess) return e;
-        scan_kernel<<<dim3((unsigned)(rows / kRowsPerCta) * s.chunks, b, 2), kThreads, sizeof(ScanSmem), st>>>(s);
+        const long long row_blocks = (long long)b * (s.blocks0 + s.blocks1);
+        const unsigned ctas = (unsigned)(s.n_whole + (row_blocks - s.n_whole) * s.chunks);
+        scan_kernel<<<ctas, kThreads, sizeof(ScanSmem), st>>>(s);
     }
     return cudaGetLastError();
 }

@@ -39,7 +39,7 @@ def _worker(rank, world, port, b, n, m, out_q):
         pts = synth.random_points(b, 3000, 43)
         tri = g.tri_forward(*(sharding.shard(t, rank, world).to(dev).contiguous() for t in (pts, t1, t2, t3)))
         torch.cuda.synchronize()
-        out_q.put((rank, i1.cpu(), i2.cpu(), float(loss), a.grad.cpu(), tuple(t.cpu() for t in tri)))
+        out_q.put((rank, i1.cpu(), i2.cpu(), float(loss.detach()), a.grad.cpu(), tuple(t.cpu() for t in tri)))
     finally:
         dist.destroy_process_group()
 
@@ -73,8 +73,9 @@ def test_sharded_path_on_two_gpus(cuda, b):
     want.backward()
     assert torch.equal(torch.cat([r[1] for r in res]), i1.cpu()) and torch.equal(torch.cat([r[2] for r in res]), i2.cpu())
     for r in res:
-        assert abs(r[3] - float(want)) <= 1e-6 * abs(float(want)), (r[3], float(want))
-    assert torch.allclose(torch.cat([r[4] for r in res]), x1.grad.cpu(), rtol=1e-6, atol=0)
+        assert abs(r[3] - float(want.detach())) <= 1e-6 * abs(float(want.detach())), (r[3], float(want.detach()))
+    # scatter-adds of the backward are fp32 atomics: order-dependent in the last bits
+    assert torch.allclose(torch.cat([r[4] for r in res]), x1.grad.cpu(), rtol=1e-5, atol=1e-7)
     v, f = synth.uv_sphere(32, 15)
     t1, t2, t3 = synth.face_vertices(synth.mesh_batch(v, b), f)
     pts = synth.random_points(b, 3000, 43)
