@@ -47,6 +47,7 @@ SYMBOLS = {
     "geom_chamfer_fwd_host": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _u]),
     "geom_chamfer_loss_workspace_bytes": (_sz, [_i, _i, _i]),
     "geom_chamfer_loss_fwd": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "geom_chamfer_loss_f1_fwd": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, C.c_float, C.c_float, _vp, _vp, _vp, _sz, _vp]),
     "geom_chamfer_loss_bwd": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "geom_debug_set": (_i, [_i, C.c_float]),
     "geom_tri_workspace_bytes": (_sz, [_i, _i]),

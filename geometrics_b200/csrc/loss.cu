@@ -25,30 +25,55 @@ __device__ __forceinline__ float warp_sum(float v)
 }
 
 // partial[blockIdx.x] = { sum_j ||xyz2[idx1[j]] - xyz1[j]||^2 , sum_k ||xyz1[idx2[k]] - xyz2[k]||^2 }
-// over this block's grid-stride share; optionally the per-point squared distances too.
+// over this block's grid-stride share; optionally the per-point squared distances too, and (F1, utils.py:424-436) the
+// per-item counts of points whose distance on f1_scale-scaled coordinates is <= f1_thr, evaluated like the reference
+// expression sqrt(sum((s*q - s*p)**2)) <= thr: every product and sum rounded separately, IEEE sqrt.
 __global__ void __launch_bounds__(kThreads)
 loss_partial_kernel(int b, int n, const float *__restrict__ xyz1, int m, const float *__restrict__ xyz2,
                     const int *__restrict__ idx1, const int *__restrict__ idx2,
-                    float *__restrict__ d1_out, float *__restrict__ d2_out, double2 *__restrict__ partial)
+                    float *__restrict__ d1_out, float *__restrict__ d2_out, double2 *__restrict__ partial,
+                    float f1_scale, float f1_thr, int *__restrict__ cnt1, int *__restrict__ cnt2)
 {
     const long long rows1 = (long long)b * n, rows2 = (long long)b * m;
+    const int lane = threadIdx.x & 31;
     float s1 = 0.f, s2 = 0.f;
-    for (long long t = (long long)blockIdx.x * kThreads + threadIdx.x; t < rows1 + rows2;
-         t += (long long)gridDim.x * kThreads) {
-        const bool first = t < rows1;
-        const long long r = first ? t : t - rows1;
-        const int cnt = first ? n : m, ocnt = first ? m : n;
-        const int bi = (int)(r / cnt);
-        const float *p = (first ? xyz1 : xyz2) + r * 3;
-        const int k = (first ? idx1 : idx2)[r];
-        const float *q = (first ? xyz2 : xyz1) + ((long long)bi * ocnt + k) * 3;
-        const float d = sqdist_ref(p[0], p[1], p[2], q[0], q[1], q[2]);
-        if (first) {
-            s1 += d;
-            if (d1_out) d1_out[r] = d;
-        } else {
-            s2 += d;
-            if (d2_out) d2_out[r] = d;
+    // warp-uniform trip count: the F1 counts are aggregated per warp before they touch memory
+    for (long long base = (long long)blockIdx.x * kThreads + (threadIdx.x & ~31); base < rows1 + rows2;
+         base += (long long)gridDim.x * kThreads) {
+        const long long t = base + lane;
+        const bool active = t < rows1 + rows2;
+        bool first = true, hit = false;
+        int bi = 0;
+        if (active) {
+            first = t < rows1;
+            const long long r = first ? t : t - rows1;
+            const int cnt = first ? n : m, ocnt = first ? m : n;
+            bi = (int)(r / cnt);
+            const float *p = (first ? xyz1 : xyz2) + r * 3;
+            const int k = (first ? idx1 : idx2)[r];
+            const float *q = (first ? xyz2 : xyz1) + ((long long)bi * ocnt + k) * 3;
+            const float px = p[0], py = p[1], pz = p[2], qx = q[0], qy = q[1], qz = q[2];
+            const float d = sqdist_ref(px, py, pz, qx, qy, qz);
+            if (first) {
+                s1 += d;
+                if (d1_out) d1_out[r] = d;
+            } else {
+                s2 += d;
+                if (d2_out) d2_out[r] = d;
+            }
+            if (cnt1) {
+                const float tx = __fsub_rn(__fmul_rn(f1_scale, qx), __fmul_rn(f1_scale, px));
+                const float ty = __fsub_rn(__fmul_rn(f1_scale, qy), __fmul_rn(f1_scale, py));
+                const float tz = __fsub_rn(__fmul_rn(f1_scale, qz), __fmul_rn(f1_scale, pz));
+                const float ss = __fadd_rn(__fadd_rn(__fmul_rn(tx, tx), __fmul_rn(ty, ty)), __fmul_rn(tz, tz));
+                hit = __fsqrt_rn(ss) <= f1_thr;
+            }
+        }
+        if (cnt1) {
+            const int key = active ? (bi * 2 + (first ? 0 : 1)) : -1;
+            const unsigned peers = __match_any_sync(0xffffffffu, key);
+            const unsigned hits = __ballot_sync(0xffffffffu, hit) & peers;
+            if (active && hits && lane == __ffs((int)peers) - 1) atomicAdd((first ? cnt1 : cnt2) + bi, __popc(hits));
         }
     }
     __shared__ float sh[2][kThreads / 32];
@@ -147,15 +172,20 @@ extern "C" size_t geom_chamfer_loss_workspace_bytes(int b, int n, int m)
     return sizeof(double2) * (size_t)loss::blocks_for((long long)b * ((long long)n + m));
 }
 
-extern "C" int geom_chamfer_loss_fwd(int b, int n, const float *xyz1, int m, const float *xyz2,
-                                     const int *idx1, const int *idx2, float *dist1, float *dist2,
-                                     float *sums, void *workspace, size_t workspace_bytes,
-                                     geom_stream_t stream)
+static int chamfer_loss_fwd_impl(int b, int n, const float *xyz1, int m, const float *xyz2, const int *idx1, const int *idx2,
+                                 float *dist1, float *dist2, float *sums, float f1_scale, float f1_thr, int *count1, int *count2,
+                                 void *workspace, size_t workspace_bytes, geom_stream_t stream)
 {
     using namespace geom::loss;
     if (b < 0 || n < 0 || m < 0 || !sums) return GEOM_ERR_INVALID_ARG;
+    if ((count1 == nullptr) != (count2 == nullptr)) return GEOM_ERR_INVALID_ARG;
     if ((long long)b * n * 3 > 0x7fffffffLL || (long long)b * m * 3 > 0x7fffffffLL) return GEOM_ERR_INVALID_ARG;
     cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaSuccess;
+    if (count1 && b > 0) {
+        if ((e = cudaMemsetAsync(count1, 0, sizeof(int) * (size_t)b, st)) != cudaSuccess) return status_from_cuda(e);
+        if ((e = cudaMemsetAsync(count2, 0, sizeof(int) * (size_t)b, st)) != cudaSuccess) return status_from_cuda(e);
+    }
     const long long items = (long long)b * ((long long)n + m);
     // a direction with no neighbours to gather from contributes nothing (reference: empty index_select)
     if (items == 0 || n == 0 || m == 0) return status_from_cuda(cudaMemsetAsync(sums, 0, 2 * sizeof(float), st));
@@ -165,11 +195,30 @@ extern "C" int geom_chamfer_loss_fwd(int b, int n, const float *xyz1, int m, con
         return GEOM_ERR_WORKSPACE;
     {
         prof::Scope ps(st, prof::kChamferLoss);
-        loss_partial_kernel<<<blocks, kThreads, 0, st>>>(b, n, xyz1, m, xyz2, idx1, idx2, dist1, dist2,
-                                                         (double2 *)workspace);
+        loss_partial_kernel<<<blocks, kThreads, 0, st>>>(b, n, xyz1, m, xyz2, idx1, idx2, dist1, dist2, (double2 *)workspace,
+                                                         f1_scale, f1_thr, count1, count2);
         loss_final_kernel<<<1, 256, 0, st>>>((const double2 *)workspace, blocks, sums);
     }
     return status_from_cuda(cudaGetLastError());
+}
+
+extern "C" int geom_chamfer_loss_fwd(int b, int n, const float *xyz1, int m, const float *xyz2,
+                                     const int *idx1, const int *idx2, float *dist1, float *dist2,
+                                     float *sums, void *workspace, size_t workspace_bytes,
+                                     geom_stream_t stream)
+{
+    return chamfer_loss_fwd_impl(b, n, xyz1, m, xyz2, idx1, idx2, dist1, dist2, sums, 0.f, 0.f, nullptr, nullptr, workspace,
+                                 workspace_bytes, stream);
+}
+
+extern "C" int geom_chamfer_loss_f1_fwd(int b, int n, const float *xyz1, int m, const float *xyz2, const int *idx1,
+                                        const int *idx2, float *dist1, float *dist2, float *sums, float f1_scale,
+                                        float f1_threshold, int *count1, int *count2, void *workspace, size_t workspace_bytes,
+                                        geom_stream_t stream)
+{
+    if (!count1 || !count2) return GEOM_ERR_INVALID_ARG;
+    return chamfer_loss_fwd_impl(b, n, xyz1, m, xyz2, idx1, idx2, dist1, dist2, sums, f1_scale, f1_threshold, count1, count2,
+                                 workspace, workspace_bytes, stream);
 }
 
 extern "C" int geom_chamfer_loss_bwd(int b, int n, const float *xyz1, int m, const float *xyz2,

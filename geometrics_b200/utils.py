@@ -188,7 +188,8 @@ class ChamferLossFunction(torch.autograd.Function):
     indices held constant (what autograd gives for utils.py:413-417)."""
 
     @staticmethod
-    def forward(ctx, xyz1, xyz2, idx1, idx2):
+    def forward(ctx, xyz1, xyz2, idx1, idx2, f1=None):
+        """``f1`` = (scale, threshold): also return the per-item F1 counts (B,) int32 x 2 from the same launch."""
         L = _lib.lib()
         a, c = xyz1.detach().contiguous(), xyz2.detach().contiguous()
         b, n, _ = a.shape
@@ -198,14 +199,24 @@ class ChamferLossFunction(torch.autograd.Function):
             sums = torch.empty(2, dtype=torch.float32, device=dev)
             wsb = L.geom_chamfer_loss_workspace_bytes(b, n, m)
             ws = torch.empty(max(wsb // 16, 1) * 2, dtype=torch.float64, device=dev)
-            _lib.check(L.geom_chamfer_loss_fwd(b, n, a.data_ptr(), m, c.data_ptr(), idx1.data_ptr(), idx2.data_ptr(),
-                                               None, None, sums.data_ptr(), ws.data_ptr(), ws.numel() * 8,
-                                               _lib.current_stream_ptr(dev)), "geom_chamfer_loss_fwd")
+            if f1 is None:
+                _lib.check(L.geom_chamfer_loss_fwd(b, n, a.data_ptr(), m, c.data_ptr(), idx1.data_ptr(), idx2.data_ptr(),
+                                                   None, None, sums.data_ptr(), ws.data_ptr(), ws.numel() * 8,
+                                                   _lib.current_stream_ptr(dev)), "geom_chamfer_loss_fwd")
+            else:
+                cnt = torch.empty(2, b, dtype=torch.int32, device=dev)
+                _lib.check(L.geom_chamfer_loss_f1_fwd(b, n, a.data_ptr(), m, c.data_ptr(), idx1.data_ptr(), idx2.data_ptr(),
+                                                      None, None, sums.data_ptr(), float(f1[0]), float(f1[1]),
+                                                      cnt[0].data_ptr(), cnt[1].data_ptr(), ws.data_ptr(), ws.numel() * 8,
+                                                      _lib.current_stream_ptr(dev)), "geom_chamfer_loss_f1_fwd")
         ctx.save_for_backward(a, c, idx1, idx2)
-        return sums
+        if f1 is None:
+            return sums
+        ctx.mark_non_differentiable(cnt)
+        return sums, cnt
 
     @staticmethod
-    def backward(ctx, grad_sums):
+    def backward(ctx, grad_sums, *_):
         a, c, idx1, idx2 = ctx.saved_tensors
         L = _lib.lib()
         b, n, _ = a.shape
@@ -220,42 +231,54 @@ class ChamferLossFunction(torch.autograd.Function):
                                                w.data_ptr(), g1.data_ptr() if need1 else None,
                                                g2.data_ptr() if need2 else None, _lib.current_stream_ptr(dev)),
                        "geom_chamfer_loss_bwd")
-        return g1, g2, None, None
+        return g1, g2, None, None, None
 
 
-def chamfer_loss_sums(xyz1: torch.Tensor, xyz2: torch.Tensor):
-    """NN search + loss sums: -> (sums (2,) differentiable, idx1 (B,n), idx2 (B,m))."""
+F1_SCALE, F1_THRESHOLD = 0.57, 1e-2  # utils.py:425-426, :490-491
+
+
+def chamfer_loss_sums(xyz1: torch.Tensor, xyz2: torch.Tensor, f1: bool = False):
+    """NN search + loss sums: -> (sums (2,) differentiable, idx1 (B,n), idx2 (B,m)); with ``f1`` also the per-item
+    F1 counts (2,B) int32 (rows of xyz1 / of xyz2 within the threshold of their neighbour) from the same launch."""
     _, idx1, _, idx2 = chamfer_forward(xyz1, xyz2, want_dist=False)
-    return ChamferLossFunction.apply(xyz1, xyz2, idx1, idx2), idx1, idx2
+    if not f1:
+        return ChamferLossFunction.apply(xyz1, xyz2, idx1, idx2), idx1, idx2
+    sums, cnt = ChamferLossFunction.apply(xyz1, xyz2, idx1, idx2, (F1_SCALE, F1_THRESHOLD))
+    return sums, idx1, idx2, cnt
 
 
-def _f_score(gt_points, pred_points, idx_p, idx_g, num):
-    """F1 at 1e-2 on 0.57-scaled coordinates (utils.py:424-436), without the per-item Python loop."""
-    b = gt_points.shape[0]
-    pred_counters = torch.gather(pred_points, 1, idx_p.long().unsqueeze(-1).expand(-1, -1, 3))
-    gt_counters = torch.gather(gt_points, 1, idx_g.long().unsqueeze(-1).expand(-1, -1, 3))
-    dist_to_pred = torch.sqrt(torch.sum((.57 * pred_counters - .57 * gt_points) ** 2, dim=-1))
-    dist_to_gt = torch.sqrt(torch.sum((.57 * gt_counters - .57 * pred_points) ** 2, dim=-1))
-    recall = (dist_to_pred <= 1e-2).sum(1).double() / float(num)
-    precision = (dist_to_gt <= 1e-2).sum(1).double() / float(num)
-    return float((2 * (precision * recall) / (precision + recall + 1e-8)).sum() / b)
+def f_score_from_counts(cnt: torch.Tensor, num: int) -> torch.Tensor:
+    """F1 (utils.py:428-436) from the fused counts: cnt[0] = ground-truth points whose nearest prediction is within
+    the threshold (recall), cnt[1] = predictions near the ground truth (precision), both divided by ``num`` as the
+    reference does.  Returns a 0-d float64 DEVICE tensor: nothing synchronises until the caller reads it
+    (``float(f)``, formatting, comparison) -- the reference returned a Python float after B host syncs."""
+    recall = cnt[0].double() / float(num)
+    precision = cnt[1].double() / float(num)
+    return (2 * (precision * recall) / (precision + recall + 1e-8)).sum() / cnt.shape[1]
 
 
-def batch_point_to_point(pred_vert, adj_info, gt_points, num=1000, f1=False, group=None):
+def _draws(sample_draws):
+    if sample_draws is None:
+        return {}
+    choices, r1, r2 = sample_draws
+    return {"choices": choices, "r1": r1, "r2": r2}
+
+
+def batch_point_to_point(pred_vert, adj_info, gt_points, num=1000, f1=False, group=None, sample_draws=None):
     """Chamfer loss between ``num`` surface samples of the predicted meshes and the ground-truth
     points (utils.py:393-438): ``(dist_1 + dist_2) * 3000`` [, f_score].  With ``group`` the batch is
     taken to be sharded over that process group and the means are global (one all-reduce of two
-    scalars)."""
-    pred_points = batch_sample(pred_vert, adj_info["faces"], num=num)
+    scalars).  ``sample_draws`` = (choices, r1, r2) replaces the sampler's random draws (parity tests)."""
+    pred_points = batch_sample(pred_vert, adj_info["faces"], num=num, **_draws(sample_draws))
     gt = gt_points.contiguous()
-    sums, id_p, id_g = chamfer_loss_sums(gt, pred_points)
+    sums, id_p, id_g, *cnt = chamfer_loss_sums(gt, pred_points, f1=f1)
     sums = all_reduce_sums(sums, group)
     ws = world_size(group)
     dist_2 = sums[0] / float(gt.shape[0] * gt.shape[1] * ws)                    # utils.py:417
     dist_1 = sums[1] / float(pred_points.shape[0] * pred_points.shape[1] * ws)  # utils.py:416
     loss = (dist_1 + dist_2) * 3000
     if f1:
-        return loss, _f_score(gt, pred_points.detach(), id_p, id_g, num)
+        return loss, f_score_from_counts(cnt[0], num)
     return loss
 
 
@@ -309,13 +332,13 @@ def point_to_surface_sum(gt_points, pred_vert, faces):
     return TriLossFunction.apply(gt, pred_vert, faces, option, index), option, index
 
 
-def batch_point_to_surface(pred_vert, adj_info, gt_points, num=1000, f1=False, group=None):
+def batch_point_to_surface(pred_vert, adj_info, gt_points, num=1000, f1=False, group=None, sample_draws=None):
     """Training loss (utils.py:441-502): Chamfer term from the surface samples to the ground truth
     plus point-to-surface term from the ground truth to the predicted triangles,
-    ``(dist_1 + dist_2) * 3000`` [, f_score]."""
-    pred_points = batch_sample(pred_vert, adj_info["faces"], num=num)
+    ``(dist_1 + dist_2) * 3000`` [, f_score].  ``sample_draws`` as in :func:`batch_point_to_point`."""
+    pred_points = batch_sample(pred_vert, adj_info["faces"], num=num, **_draws(sample_draws))
     gt = gt_points.contiguous()
-    sums, id_p, id_g = chamfer_loss_sums(gt, pred_points)
+    sums, id_p, id_g, *cnt = chamfer_loss_sums(gt, pred_points, f1=f1)
     tri_sum, _, _ = point_to_surface_sum(gt, pred_vert, adj_info["faces"])
     part = all_reduce_sums(torch.cat((sums[1:2], tri_sum)), group)
     ws = world_size(group)
@@ -323,7 +346,7 @@ def batch_point_to_surface(pred_vert, adj_info, gt_points, num=1000, f1=False, g
     dist_2 = part[1] / float(gt.shape[0] * gt.shape[1] * ws)                    # utils.py:481, 549
     loss = (dist_1 + dist_2) * 3000
     if f1:
-        return loss, _f_score(gt, pred_points.detach(), id_p, id_g, num)
+        return loss, f_score_from_counts(cnt[0], num)
     return loss
 
 

@@ -146,6 +146,14 @@ GEOM_API size_t geom_chamfer_loss_workspace_bytes(int b, int n, int m);
 GEOM_API int geom_chamfer_loss_fwd(int b, int n, const float *xyz1, int m, const float *xyz2,
                           const int *idx1, const int *idx2, float *dist1, float *dist2, float *sums,
                           void *workspace, size_t workspace_bytes, geom_stream_t stream);
+/* The same with the F1 counts of utils.py:424-436 / :489-500 fused in: count1[i] = number of rows j of
+ * item i of xyz1 with sqrt(sum((s*xyz2[idx1[j]] - s*xyz1[j])**2)) <= threshold (s = f1_scale; the reference uses s = 0.57,
+ * threshold = 1e-2), count2[i] likewise for xyz2's rows; (B,) int32 each, overwritten.  The caller turns them into
+ * recall / precision (count / num) and F1 -- on the device, so nothing synchronises until the value is read. */
+GEOM_API int geom_chamfer_loss_f1_fwd(int b, int n, const float *xyz1, int m, const float *xyz2,
+                             const int *idx1, const int *idx2, float *dist1, float *dist2, float *sums,
+                             float f1_scale, float f1_threshold, int *count1, int *count2,
+                             void *workspace, size_t workspace_bytes, geom_stream_t stream);
 GEOM_API int geom_chamfer_loss_bwd(int b, int n, const float *xyz1, int m, const float *xyz2,
                           const int *idx1, const int *idx2, const float *weights,
                           float *grad1, float *grad2, geom_stream_t stream);
