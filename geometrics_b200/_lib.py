@@ -72,6 +72,10 @@ SYMBOLS = {
     "geom_zeron_gcn_tensor_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "geom_zeron_gcn_fwd": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
     "geom_zeron_gcn_bwd_smooth": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "geom_zeron_gcn_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "geom_zeron_gcn_bwd": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
+    "geom_bn_relu_res_fwd": (_i, [_i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, C.c_float, C.c_float, _vp, _vp, _vp, _vp]),
+    "geom_bn_relu_res_bwd": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
 }
 
 

@@ -249,7 +249,9 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 bot
         int cnt = 0;
         const float rmax = __uint_as_float(*both.rmax_bits);
         // |dt - d| <= eps; inputs too large for the bf16 split to stay finite disable the filter (eps = inf)
-        const float eps2 = (rmax < 1.0e15f) ? 2.0f * both.eps_scale * rmax * rmax : __int_as_float(0x7f800000);
+        // (padding candidates carry a norm of kBigNorm = 1e30: they can only stay above every real approximate distance
+        // while 12 R^2 << 1e30, hence the 1e13 bound)
+        const float eps2 = (rmax < 1.0e13f) ? 2.0f * both.eps_scale * rmax * rmax : __int_as_float(0x7f800000);
         // candidate indices are local to this CTA's tile range inside the sweep (tile0 is added back at the end)
         const float *cb = a.cxyz + ((size_t)bi * a.nc_full + (size_t)tile0 * kTileCols) * 3;
         const int nc_loc = a.nc - tile0 * kTileCols, nc_full_loc = a.nc_full - tile0 * kTileCols;

@@ -113,6 +113,12 @@ extern "C" int geom_chamfer_fwd_host(geom_host_ctx *c, int b, int n, const float
                                      int *h_idx2, int chunks, unsigned flags)
 {
     if (!c || b < 0 || n < 0 || m < 0) return GEOM_ERR_INVALID_ARG;
+    {
+        // the context's streams, events and arena live on the device it was created on: calling from another current
+        // device would launch there with pointers from here
+        int cur = -1;
+        if (cudaGetDevice(&cur) != cudaSuccess || cur != c->device) return GEOM_ERR_INVALID_ARG;
+    }
     if (b == 0 || (n == 0 && m == 0)) return GEOM_OK;
     if ((n > 0 && (!h_xyz1 || !h_idx1)) || (m > 0 && (!h_xyz2 || !h_idx2))) return GEOM_ERR_INVALID_ARG;
     int lo_of[geom_host_ctx::kMaxChunks + 1];

@@ -138,7 +138,7 @@ class ZeroNGCNFunction(torch.autograd.Function):
                                             ws.data_ptr(), ws.numel() * 4, _lib.current_stream_ptr(dev)),
                        "geom_zeron_gcn_fwd")
         ctx.save_for_backward(xc, wc, y if relu else None)
-        ctx.csr, ctx.ksplit, ctx.has_bias = csr, ksplit, bias is not None
+        ctx.csr, ctx.ksplit, ctx.has_bias, ctx.tensor = csr, ksplit, bias is not None, bool(tensor)
         return y
 
     @staticmethod
@@ -150,20 +150,86 @@ class ZeroNGCNFunction(torch.autograd.Function):
         if y is not None:
             dy = dy * (y > 0)
         b, v, fout = dy.shape
+        fin = xc.shape[2]
         dev = dy.device
+        need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
         with torch.cuda.device(dev):
-            ds = torch.empty_like(dy)
-            _lib.check(L.geom_zeron_gcn_bwd_smooth(b, v, fout, ksplit, csr.t_row_ptr.data_ptr(), csr.t_col_idx.data_ptr(),
-                                                   csr.t_val.data_ptr(), dy.data_ptr(), ds.data_ptr(),
-                                                   _lib.current_stream_ptr(dev)), "geom_zeron_gcn_bwd_smooth")
-        dx = dw = db = None
-        if ctx.needs_input_grad[0]:
-            dx = torch.matmul(ds, wc.t())                                   # plain library GEMM
-        if ctx.needs_input_grad[1]:
-            dw = torch.matmul(xc.reshape(-1, xc.shape[-1]).t(), ds.reshape(-1, fout))
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = dy.sum(dim=(0, 1))
+            dx = torch.empty_like(xc) if need_x else None
+            dw = torch.empty_like(wc) if need_w else None
+            db = torch.empty(fout, dtype=torch.float32, device=dev) if need_b else None
+            wsb = L.geom_zeron_gcn_bwd_workspace_bytes(b, v, fin, fout)
+            ws = torch.empty(wsb // 4 + 4, dtype=torch.float32, device=dev)
+            # dS = adj^T-smoothed dY, db = column sums, dW = X^T dS, dX = dS W^T: all in this library (gcn_bwd.cu)
+            _lib.check(L.geom_zeron_gcn_bwd(b, v, fin, fout, ksplit, xc.data_ptr(), wc.data_ptr(), dy.data_ptr(),
+                                            csr.t_row_ptr.data_ptr(), csr.t_col_idx.data_ptr(), csr.t_val.data_ptr(),
+                                            dx.data_ptr() if need_x else None, dw.data_ptr() if need_w else None,
+                                            db.data_ptr() if need_b else None, 2 if ctx.tensor else 0,
+                                            ws.data_ptr(), ws.numel() * 4, _lib.current_stream_ptr(dev)), "geom_zeron_gcn_bwd")
         return dx, dw, db, None, None, None, None
+
+
+class BnReluResFunction(torch.autograd.Function):
+    """out = relu(batch_norm_over_vertices(x)) or (res + that) / 2 -- ``geom_bn_relu_res_fwd / _bwd`` (bn.cu): the
+    BatchNorm1d(V) + ReLU + averaged-residual stage of BatchMeshDeformationBlock (models.py:241-294) in one launch."""
+
+    @staticmethod
+    def forward(ctx, x, res, gamma, beta, running_mean, running_var, batches_tracked, training, momentum, eps):
+        L = _lib.lib()
+        xc = x.detach().contiguous()
+        b, v, c = xc.shape
+        dev = xc.device
+        ld_res = 0
+        if res is not None:
+            if res.shape != xc.shape or res.stride(2) != 1 or res.stride(0) != v * res.stride(1):
+                res = res.contiguous()
+            ld_res = res.stride(1)
+        with torch.cuda.device(dev):
+            out = torch.empty_like(xc)
+            stats = torch.empty(2, v, dtype=torch.float32, device=dev)
+            ptr = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
+            _lib.check(L.geom_bn_relu_res_fwd(b, v, c, xc.data_ptr(), ptr(res), ld_res, ptr(gamma), ptr(beta), ptr(running_mean),
+                                              ptr(running_var), ptr(batches_tracked), int(training), float(momentum), float(eps),
+                                              stats[0].data_ptr(), stats[1].data_ptr(), out.data_ptr(),
+                                              _lib.current_stream_ptr(dev)), "geom_bn_relu_res_fwd")
+        ctx.save_for_backward(xc, gamma, beta, stats)
+        ctx.training, ctx.has_res = bool(training), res is not None
+        return out  # (the running statistics are plain buffers updated in place by the kernel, as F.batch_norm does)
+
+    @staticmethod
+    def backward(ctx, dout):
+        xc, gamma, beta, stats = ctx.saved_tensors
+        L = _lib.lib()
+        dout = dout.contiguous()
+        b, v, c = xc.shape
+        dev = xc.device
+        need_res = ctx.has_res and ctx.needs_input_grad[1]
+        with torch.cuda.device(dev):
+            dx = torch.empty_like(xc)
+            dres = torch.empty_like(xc) if need_res else None
+            dg = torch.empty(v, dtype=torch.float32, device=dev) if gamma is not None else None
+            dbt = torch.empty(v, dtype=torch.float32, device=dev) if beta is not None else None
+            ptr = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
+            _lib.check(L.geom_bn_relu_res_bwd(b, v, c, xc.data_ptr(), dout.data_ptr(), ptr(gamma), ptr(beta), stats[0].data_ptr(),
+                                              stats[1].data_ptr(), int(ctx.training), int(ctx.has_res), dx.data_ptr(), ptr(dres),
+                                              ptr(dg), ptr(dbt), _lib.current_stream_ptr(dev)), "geom_bn_relu_res_bwd")
+        return dx, dres, dg, dbt, None, None, None, None, None, None
+
+
+def bn_relu_res(x, bn: nn.BatchNorm1d, res=None):
+    """``F.relu(bn(x))`` for x (B,V,C) and ``bn = nn.BatchNorm1d(V)`` [then ``(res + .) / 2``], fused.  The module only
+    supplies its parameters and buffers (state-dict compatible); semantics follow torch's BatchNorm1d exactly: batch
+    statistics in training mode (or when it tracks no running statistics), running statistics updated in place."""
+    _lib.require_cuda_f32("x", x)
+    if x.dim() != 3 or x.shape[1] != bn.num_features:
+        raise ValueError(f"expected (B, {bn.num_features}, C), got {tuple(x.shape)}")
+    use_batch = bn.training or bn.running_mean is None
+    momentum = bn.momentum
+    if momentum is None:  # cumulative moving average
+        momentum = 1.0 / float(int(bn.num_batches_tracked) + 1) if bn.num_batches_tracked is not None else 0.0
+    track = bn.training and bn.track_running_stats
+    return BnReluResFunction.apply(x, res, bn.weight, bn.bias, bn.running_mean if (track or not use_batch) else None,
+                                   bn.running_var if (track or not use_batch) else None,
+                                   bn.num_batches_tracked if track else None, use_batch, momentum, bn.eps)
 
 
 TENSOR_GEMM = True  # feature GEMM on the tensor cores (3xTF32 tcgen05) whenever the shape allows (out >= 16, <= 256)

@@ -11,7 +11,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from .layers import (BatchGCNMax, BatchZERON_GCN, Batch_Image_ZERON_GCNGCN, GCNMax, Image_ZERON_GCNGCN,
-                     ZERON_GCN, csr_from_dense)
+                     ZERON_GCN, bn_relu_res, csr_from_dense)
 
 _identity = None  # activation=None means identity in layers.zeron_gcn
 
@@ -29,21 +29,19 @@ class _DeformationStack(nn.Module):
     layer_cls = None
     feature_dim = -1
 
-    def _gcn(self, i, x, adj):
+    def _gcn(self, i, x, adj, res=None):
+        """Layer i with its normalisation / activation; with ``res`` also the averaged residual (res + .) / 2."""
         raise NotImplementedError
 
     def forward(self, features, pooled, adj):
         adj = _as_csr(adj)
         full_features = torch.cat((features, pooled), dim=self.feature_dim)
         x = self._gcn(1, full_features, adj)
-        x = self._gcn(2, x, adj)
-        features = (full_features[..., :self.hidden] + x) / 2
+        features = self._gcn(2, x, adj, res=full_features[..., :self.hidden])   # models.py:246-248
         for i in (3, 5, 7, 9, 11):
             x = self._gcn(i, features, adj)
-            x = self._gcn(i + 1, x, adj)
-            features = (features + x) / 2
-        x = self._gcn(13, features, adj)
-        features = (features + x) / 2
+            features = self._gcn(i + 1, x, adj, res=features)                   # :255-256 ...
+        features = self._gcn(13, features, adj, res=features)                   # :290-294
         coords = self.gc15(features, adj, _identity)
         return features, coords
 
@@ -62,9 +60,15 @@ class BatchMeshDeformationBlock(_DeformationStack):
         for i in range(1, 15):
             setattr(self, f"bn{i}", nn.BatchNorm1d(verts))
 
-    def _gcn(self, i, x, adj):
+    FUSED_BN = True  # BatchNorm1d(V) + ReLU + residual average in one kernel (bn.cu); False: the torch modules
+
+    def _gcn(self, i, x, adj, res=None):
         x = getattr(self, f"gc{i}")(x, adj, _identity)
-        return F.relu(getattr(self, f"bn{i}")(x))
+        bn = getattr(self, f"bn{i}")
+        if self.FUSED_BN and x.is_cuda and x.dim() == 3:
+            return bn_relu_res(x, bn, res)
+        x = F.relu(bn(x))
+        return x if res is None else (res + x) / 2
 
 
 class MeshDeformationBlock(_DeformationStack):
@@ -80,8 +84,9 @@ class MeshDeformationBlock(_DeformationStack):
         self.gc15 = Image_ZERON_GCNGCN(hidden, output_features)
         self.hidden = hidden
 
-    def _gcn(self, i, x, adj):
-        return getattr(self, f"gc{i}")(x, adj, F.relu)
+    def _gcn(self, i, x, adj, res=None):
+        x = getattr(self, f"gc{i}")(x, adj, F.relu)
+        return x if res is None else (res + x) / 2
 
 
 _ENCODER_DIMS = [("h1", 3, 60), ("h21", 60, 60), ("h22", 60, 60), ("h23", 60, 60), ("h24", 60, 120),

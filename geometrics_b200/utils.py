@@ -149,7 +149,12 @@ def batch_sample(verts: torch.Tensor, faces: torch.Tensor, num: int = 10000, *, 
 # Chamfer loss
 # ------------------------------------------------------------------------------------------------
 class _AllReduceSum(torch.autograd.Function):
-    """Sum partial loss sums over the ranks of ``group``; every rank keeps the same upstream gradient."""
+    """Sum partial loss sums over the ranks of ``group``; every rank keeps the same upstream gradient.
+
+    Gradient convention: every rank ends up with d(GLOBAL-mean loss)/d(its own points and parameters) -- the backward
+    passes the upstream gradient through unchanged.  Summing parameter gradients over ranks (all-reduce SUM) therefore
+    gives the exact gradient of the global mean; DistributedDataParallel AVERAGES over ranks, which yields 1/W of it:
+    scale the loss by the world size (or the learning rate) when training under DDP with ``group=``."""
 
     @staticmethod
     def forward(ctx, sums, group):
@@ -408,13 +413,19 @@ def batch_get_lap_info(positions, adj_info):
     becomes a CSR SpMM over the three coordinate columns."""
     from .layers import csr_matmul
 
+    import weakref
+
     orig = adj_info["adj_orig"]
     key = (orig.data_ptr(), orig._version, orig.shape[0])
-    scaler = _degree_cache.get(key)
+    hit = _degree_cache.get(key)
+    # an entry is valid only while the tensor it was computed from is alive: the allocator can hand the same address
+    # (and version 0) to a different adjacency of the same size
+    scaler = hit[1] if hit is not None and hit[0]() is orig else None
     if scaler is None:
         if len(_degree_cache) > 16:
             _degree_cache.clear()
-        scaler = _degree_cache[key] = (1. / (torch.sum(orig, dim=1) - 1)).view(-1, 1)
+        scaler = (1. / (torch.sum(orig, dim=1) - 1)).view(-1, 1)
+        _degree_cache[key] = (weakref.ref(orig), scaler)
     neighbor_sum = (csr_matmul(orig, positions) - positions) * scaler
     return positions - neighbor_sum
 
@@ -548,7 +559,13 @@ class PoolFunction(torch.autograd.Function):
             _lib.check(L.geom_pool_bwd(b, v, len(maps), ptrs, gptrs, ch, dm, xs.data_ptr(), ys.data_ptr(), dout.data_ptr(),
                                        ld, col0, gxs.data_ptr() if gxs is not None else None,
                                        gys.data_ptr() if gys is not None else None, _lib.current_stream_ptr(dev)), "geom_pool_bwd")
-        return (gxs, gys, None, None, *gmaps)
+        gbuf = None
+        if ctx.needs_input_grad[2]:
+            # the pre-filled columns of the caller's buffer (e.g. the vertex positions next to the pooled features) pass
+            # their gradient straight through; the columns this op overwrote carry none
+            gbuf = dout.clone()
+            gbuf[:, :, col0:col0 + sum(chans)] = 0
+        return (gxs, gys, gbuf, None, *gmaps)
 
 
 def pool_features(blocks, xs: torch.Tensor, ys: torch.Tensor, out: torch.Tensor = None, col0: int = 0) -> torch.Tensor:

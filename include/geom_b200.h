@@ -99,7 +99,10 @@ GEOM_API int geom_debug_set(int knob, float value);
  * Ties: lowest candidate index (chamfer_distance.cu:39,47).  Arithmetic per pair:
  * fma(dz,dz, fma(dx,dx, dy*dy)) with d* = candidate - query, as nvcc compiles :35-38.
  * dist1 / dist2 may be NULL (the Python caller discards them, chamfer_distance.py:31).
- * Inputs must be finite.
+ * NaN / Inf coordinates get exactly what the reference kernel gives them (the first candidate of every 512-tile is
+ * taken unconditionally, :39, tiles merge with a strict '>', :47: a NaN distance at a tile start voids that tile and a
+ * NaN at candidate 0 sticks): every path detects non-finite inputs on the device and redoes the rows with a
+ * transcription of the reference loop (slow, exact).
  * ------------------------------------------------------------------------------------------- */
 GEOM_API size_t geom_chamfer_workspace_bytes(int b, int n, int m);
 /* workspace for the tensor-core search (packed bf16 operands: 64 B per padded point; >= the plain workspace);
@@ -114,7 +117,8 @@ GEOM_API int geom_chamfer_fwd(int b, int n, const float *xyz1, int m, const floa
  * slices (<= 8; 0 = default 4; the library sizes them): slice k+1 is copied to the device while slice k is searched and slice
  * k-1's results are copied back, on three internal streams.  Synchronous: returns when all results
  * are in host memory.  h_dist1 / h_dist2 may be NULL.  A geom_host_ctx owns the streams, events and a
- * device arena reused across calls; create one per calling thread, on the device it should use.
+ * device arena reused across calls; create one per calling thread, on the device it should use (a call made while
+ * another device is current returns GEOM_ERR_INVALID_ARG).
  * This is the end-to-end path bench.py reports as "e2e". */
 typedef struct geom_host_ctx geom_host_ctx;
 /* The slice plan geom_chamfer_fwd_host uses (pure host logic, no device access): slice k covers batch items
@@ -297,6 +301,35 @@ GEOM_API int geom_zeron_gcn_fwd(int b, int V, int in_features, int out_features,
 GEOM_API int geom_zeron_gcn_bwd_smooth(int b, int V, int out_features, int ksplit, const int *t_row_ptr,
                               const int *t_col_idx, const float *t_val, const float *dY, float *dS,
                               geom_stream_t stream);
+
+/* Whole backward of the layer (autograd of layers.py:107-116), every GEMM in this library:
+ *   dS = [adj^T . dY[:, :ksplit] | dY[:, ksplit:]],  db = column sums of dY,  dW = X^T dS,  dX = dS W^T.
+ * dX / dW / db may be NULL (not needed).  flags: GEOM_GCN_TENSOR runs dX on the tensor cores when 16 <= in <= 256.
+ * workspace >= geom_zeron_gcn_bwd_workspace_bytes, 16-byte aligned.  dW accumulates split-M partial tiles with fp32
+ * atomics (summation order varies run to run in the last bits, like cuBLAS split-K). */
+GEOM_API size_t geom_zeron_gcn_bwd_workspace_bytes(int b, int V, int in_features, int out_features);
+GEOM_API int geom_zeron_gcn_bwd(int b, int V, int in_features, int out_features, int ksplit, const float *X, const float *W,
+                       const float *dY, const int *t_row_ptr, const int *t_col_idx, const float *t_val, float *dX,
+                       float *dW, float *db, int flags, void *workspace, size_t workspace_bytes, geom_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * BatchNorm1d(V) + ReLU + averaged residual of the deformation block.
+ * Replaces, per stage of BatchMeshDeformationBlock.forward (models.py:241-294),  x = F.relu(bnK(x))  and, after the
+ * second layer of a stage,  features = (features + x) / 2  -- torch's batch_norm / relu / add / div kernels and their
+ * backward.  nn.BatchNorm1d(verts) on a (B,V,C) tensor normalises per VERTEX over the B*C values (models.py:222-235).
+ * fwd: training != 0 uses batch statistics (biased variance) and updates running_mean / running_var (momentum,
+ *   unbiased variance) and *batches_tracked (int64, may be NULL) as torch does; training == 0 uses the running
+ *   statistics.  out = relu(bn(x)) or, with res != NULL, (res + relu(bn(x))) / 2; res may be the leading C columns of a
+ *   wider (B,V,ld_res) tensor.  save_mean / save_invstd (V) are kept for the backward.
+ * bwd: dx (B,V,C); dres = dout / 2 (NULL to skip); dgamma / dbeta (V, NULL to skip).
+ * ------------------------------------------------------------------------------------------- */
+GEOM_API int geom_bn_relu_res_fwd(int b, int V, int C, const float *x, const float *res, int ld_res, const float *gamma,
+                         const float *beta, float *running_mean, float *running_var, long long *batches_tracked,
+                         int training, float momentum, float eps, float *save_mean, float *save_invstd, float *out,
+                         geom_stream_t stream);
+GEOM_API int geom_bn_relu_res_bwd(int b, int V, int C, const float *x, const float *dout, const float *gamma, const float *beta,
+                         const float *save_mean, const float *save_invstd, int training, int has_res, float *dx,
+                         float *dres, float *dgamma, float *dbeta, geom_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -282,3 +282,76 @@ def test_tensor_gemm_layer_vs_torch(cuda, shape):
         close(simt, want.cpu().numpy(), 1e-5, f"cuda-core fwd {shape}")
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+# ---------------------------------------------------------------------------- fused BatchNorm1d(V) + ReLU + residual
+@pytest.mark.parametrize("training", [True, False], ids=["train", "eval"])
+@pytest.mark.parametrize("res_kind", ["none", "dense", "slice"])
+@pytest.mark.parametrize("shape", [(16, 482, 192), (3, 37, 5), (32, 64, 256)])
+def test_bn_relu_res_matches_torch(cuda, shape, res_kind, training):
+    """geom_bn_relu_res_fwd/_bwd against nn.BatchNorm1d(V) -> F.relu -> (res + x) / 2 (models.py:241-248): outputs,
+    running statistics, num_batches_tracked, and every gradient (x, res, gamma, beta)."""
+    from geometrics_b200.layers import bn_relu_res
+
+    b, v, c = shape
+    g = torch.Generator(device=cuda).manual_seed(b * 1000 + v)
+    x0 = torch.randn(b, v, c, device=cuda, generator=g) * 2 + 0.3
+    wide0 = torch.randn(b, v, c + 7, device=cuda, generator=g)
+    up = torch.randn(b, v, c, device=cuda, generator=g)
+    outs = []
+    for fused in (False, True):
+        bn = torch.nn.BatchNorm1d(v).to(cuda)
+        with torch.no_grad():
+            bn.weight.copy_(torch.linspace(0.5, 1.5, v))
+            bn.bias.copy_(torch.linspace(-0.2, 0.2, v))
+            bn.running_mean.copy_(torch.linspace(-0.1, 0.4, v))
+            bn.running_var.copy_(torch.linspace(0.8, 2.5, v))
+        bn.train(training)
+        x = x0.clone().requires_grad_(True)
+        wide = wide0.clone().requires_grad_(True)
+        res = None if res_kind == "none" else (wide[..., :c].contiguous() if res_kind == "dense" else wide[..., :c])
+        if fused:
+            y = bn_relu_res(x, bn, res)
+        else:
+            y = torch.nn.functional.relu(bn(x))
+            y = y if res is None else (res + y) / 2
+        (y * up).sum().backward()
+        outs.append((y.detach(), x.grad, wide.grad if res is not None else torch.zeros(1, device=cuda), bn.weight.grad, bn.bias.grad,
+                     bn.running_mean.clone(), bn.running_var.clone(), bn.num_batches_tracked.clone().float()))
+    names = ("out", "dx", "dres", "dgamma", "dbeta", "running_mean", "running_var", "num_batches_tracked")
+    for name, a, r in zip(names, outs[1], outs[0]):
+        scale = max(1.0, float(r.abs().max()))
+        assert float((a - r).abs().max()) <= 2e-5 * scale, (name, float((a - r).abs().max()), scale)
+
+
+@pytest.mark.parametrize("shape", [(16, 482, 963, 192, 64), (16, 482, 192, 192, 64), (16, 482, 192, 3, 1), (2, 50, 37, 21, 7),
+                                   (4, 2562, 256, 256, 85), (3, 40, 300, 50, 5)])
+def test_gcn_backward_kernels_vs_torch(cuda, shape):
+    """geom_zeron_gcn_bwd (dS, db, dW = X^T dS, dX = dS W^T; gcn_bwd.cu) against autograd of the reference expression
+    (layers.py:110-115) with the dense adjacency, <= 1e-5 relative to each gradient's scale."""
+    import geometrics_b200 as g
+    from geometrics_b200 import synth
+
+    b, v, fin, fout, k = shape
+    gen = torch.Generator(device=cuda).manual_seed(fin * 7 + fout)
+    adj = torch.rand(v, v, device=cuda, generator=gen)
+    adj = (adj > 0.9).float() + torch.eye(v, device=cuda)
+    adj = adj / adj.sum(1, keepdim=True)
+    x0 = torch.randn(b, v, fin, device=cuda, generator=gen) * 0.3
+    w0 = torch.randn(fin, fout, device=cuda, generator=gen) / fin ** 0.5
+    b0 = torch.randn(fout, device=cuda, generator=gen)
+    up = torch.randn(b, v, fout, device=cuda, generator=gen)
+    split = fout // k if k else 1
+    grads = []
+    for ours in (False, True):
+        x, w, bias = x0.clone().requires_grad_(True), w0.clone().requires_grad_(True), b0.clone().requires_grad_(True)
+        if ours:
+            y = g.zeron_gcn(x, w, bias, adj, split)
+        else:
+            s_ = torch.matmul(x, w)
+            kk = fout // split
+            y = torch.cat((torch.matmul(adj, s_[..., :kk]), s_[..., kk:]), dim=-1) + bias
+        (y * up).sum().backward()
+        grads.append((x.grad, w.grad, bias.grad))
+    for name, a, r in zip(("dX", "dW", "db"), grads[1], grads[0]):
+        assert float((a - r).abs().max()) <= 2e-5 * max(1e-3, float(r.abs().max())), (name, float((a - r).abs().max()), float(r.abs().max()))

@@ -98,6 +98,34 @@ def test_gather_into_block_input_buffer(cuda):
     assert bool((buf[:, :, 3 + want.shape[2]:] == -7.0).all())
 
 
+def test_gather_into_buffer_keeps_the_gradient_of_the_prefilled_columns(cuda):
+    """Training pattern: buf[:, :, :3] = verts, then pool_features(..., out=buf, col0=3).  The gradient that reaches the
+    position columns of the buffer must flow back to verts (and through xs / ys and the maps as without `out`)."""
+    import geometrics_b200.utils as U
+
+    verts, img_info, blocks = G.inputs()
+    img_info = img_info.to(cuda)
+    w = None
+    grads = []
+    for use_out in (False, True):
+        v = verts.to(cuda).clone().requires_grad_(True)
+        blk = [b.to(cuda).clone().requires_grad_(True) for b in blocks]
+        xs, ys = U.project_vertices(v, img_info)
+        if use_out:
+            c = sum(b.shape[1] for b in blk)
+            buf = torch.zeros(2, 96, 3 + c, device=cuda)
+            buf[:, :, :3] = v          # in-place copy of a tensor that requires grad: buf now carries autograd history
+            full = U.pool_features(blk, xs, ys, out=buf, col0=3)
+        else:
+            full = torch.cat((v, U.pool_features(blk, xs, ys)), dim=2)
+        if w is None:
+            w = torch.randn(full.shape, device=cuda, generator=torch.Generator(device=cuda).manual_seed(5))
+        (full * w).sum().backward()
+        grads.append([v.grad] + [b.grad for b in blk])
+    for a, r in zip(*grads):
+        assert float((a - r).abs().max()) <= 2e-5 * max(1.0, float(r.abs().max())), float((a - r).abs().max())
+
+
 def test_argument_validation(cuda):
     import geometrics_b200.utils as U
 
