@@ -150,6 +150,28 @@ def require_cuda_f32(name: str, t, last=None):
         raise ValueError(f"{name} must have shape (B, N, {last}), got {tuple(t.shape)}")
 
 
+class _NoGuard:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def on_device(device):
+    """``with on_device(dev):`` -- torch.cuda.device(dev) only when dev is not already current (the context manager costs
+    ~10 us of host time per use, which adds up over the ~30 small launches of a deformation block)."""
+    import torch
+
+    idx = device.index
+    if idx is None or idx == torch.cuda.current_device():
+        return _NO_GUARD
+    return torch.cuda.device(device)
+
+
 def current_stream_ptr(device) -> int:
     import torch
 

@@ -32,7 +32,7 @@ def chamfer_forward(xyz1: torch.Tensor, xyz2: torch.Tensor, *, exact_tail: bool 
     b, n, _ = xyz1.shape
     m = xyz2.shape[1]
     dev = xyz1.device
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         idx1 = torch.empty((b, n), dtype=torch.int32, device=dev)
         idx2 = torch.empty((b, m), dtype=torch.int32, device=dev)
         dist1 = torch.empty((b, n), dtype=torch.float32, device=dev) if want_dist else None
@@ -85,7 +85,7 @@ def _ctx_for(dev: torch.device):
     ctx = _host_ctx.get(key)
     if ctx is None:
         handle = ctypes.c_void_p()
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             _lib.check(_lib.lib().geom_host_ctx_create(ctypes.byref(handle)), "geom_host_ctx_create")
         ctx = _host_ctx[key] = handle
     return ctx
@@ -124,7 +124,7 @@ def chamfer_forward_host(xyz1: torch.Tensor, xyz2: torch.Tensor, idx1_out: torch
         raise RuntimeError("no CUDA device (geometrics_b200 has no CPU path)")
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     L = _lib.lib()
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         rc = L.geom_chamfer_fwd_host(_ctx_for(dev), b, n, xyz1.data_ptr(), m, xyz2.data_ptr(),
                                      dist1_out.data_ptr() if dist1_out is not None else None, idx1_out.data_ptr(),
                                      dist2_out.data_ptr() if dist2_out is not None else None, idx2_out.data_ptr(),

@@ -10,8 +10,9 @@
 //   eval:      the running statistics instead
 //   out = relu(y)                       (res == NULL)
 //   out = (res + relu(y)) / 2           (res != NULL; res may be a column slice of a wider tensor: row stride ld_res)
-// One CTA per vertex: the vertex' B rows of C floats (B*C*4 = 12 KB at the reference's B=16, C=192) are read three times
-// from L2 (sum, centred sum of squares, normalise) -- two-pass statistics like torch's, no E[x^2]-E[x]^2 cancellation.
+// One CTA per vertex: the vertex' B rows of C floats (B*C*4 = 12 KB at the reference's B=16, C=192) are read once into
+// registers (up to 8192 values per vertex; beyond that three passes over L2): sum, centred sum of squares, normalise --
+// two-pass statistics like torch's, no E[x^2]-E[x]^2 cancellation.
 // Backward (one CTA per vertex): dy = dout * [y > 0] (x 1/2 with a residual), dgamma = sum dy xhat, dbeta = sum dy,
 //   dx = gamma invstd (dy - dbeta/N - xhat dgamma/N)     (training);   dx = gamma invstd dy     (eval)
 // and dres = dout / 2 written in the same pass.
@@ -47,6 +48,10 @@ struct FwdArgs {
     float eps, momentum;
 };
 
+// EPT > 0: the vertex' B*C values (<= 256 * EPT) are read ONCE into registers; EPT == 0: streaming fallback for any size
+// (three passes over L2).  Element i of the vertex is (b, c) = (i / C, i % C); a thread walks i = tid, tid + 256, ... by
+// stepping (b, c) with the precomputed (256 / C, 256 % C) -- no division in the loops.
+template <int EPT>
 __global__ void __launch_bounds__(kThreads) fwd_kernel(const FwdArgs a)
 {
     __shared__ float sh[kThreads / 32];
@@ -54,15 +59,49 @@ __global__ void __launch_bounds__(kThreads) fwd_kernel(const FwdArgs a)
     const int n = a.B * a.C;
     const size_t vstride = (size_t)a.V * a.C;
     const float *xv = a.x + (size_t)v * a.C;
+    const int sb = kThreads / a.C, sc = kThreads % a.C;
+    const int b0 = threadIdx.x / a.C, c0 = threadIdx.x % a.C;
+    constexpr int R = EPT > 0 ? EPT : 1;
+    float xr[R];
     float mean, invstd;
+    if (EPT > 0) {
+        int bb = b0, cc = c0;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            xr[k] = (threadIdx.x + k * kThreads < n) ? xv[(size_t)bb * vstride + cc] : 0.f;
+            bb += sb, cc += sc;
+            if (cc >= a.C) cc -= a.C, ++bb;
+        }
+    }
     if (a.training) {
         float s = 0.f;
-        for (int i = threadIdx.x; i < n; i += kThreads) s += xv[(size_t)(i / a.C) * vstride + (i % a.C)];
+        if (EPT > 0) {
+#pragma unroll
+            for (int k = 0; k < R; ++k) s += xr[k];
+        } else {
+            int bb = b0, cc = c0;
+            for (int i = threadIdx.x; i < n; i += kThreads) {
+                s += xv[(size_t)bb * vstride + cc];
+                bb += sb, cc += sc;
+                if (cc >= a.C) cc -= a.C, ++bb;
+            }
+        }
         mean = block_sum(s, sh) / (float)n;
         float q = 0.f;
-        for (int i = threadIdx.x; i < n; i += kThreads) {
-            const float d = xv[(size_t)(i / a.C) * vstride + (i % a.C)] - mean;
-            q = fmaf(d, d, q);
+        if (EPT > 0) {
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                const float d = (threadIdx.x + k * kThreads < n) ? xr[k] - mean : 0.f;
+                q = fmaf(d, d, q);
+            }
+        } else {
+            int bb = b0, cc = c0;
+            for (int i = threadIdx.x; i < n; i += kThreads) {
+                const float d = xv[(size_t)bb * vstride + cc] - mean;
+                q = fmaf(d, d, q);
+                bb += sb, cc += sc;
+                if (cc >= a.C) cc -= a.C, ++bb;
+            }
         }
         const float var = block_sum(q, sh) / (float)n;
         invstd = rsqrtf(var + a.eps);
@@ -84,11 +123,26 @@ __global__ void __launch_bounds__(kThreads) fwd_kernel(const FwdArgs a)
     float *ov = a.out + (size_t)v * a.C;
     const float *rv = a.res ? a.res + (size_t)v * a.ld_res : nullptr;
     const size_t rstride = (size_t)a.V * a.ld_res;
-    for (int i = threadIdx.x; i < n; i += kThreads) {
-        const int b = i / a.C, c = i % a.C;
-        float y = fmaxf(fmaf(xv[(size_t)b * vstride + c], scale, shift), 0.f);
-        if (rv) y = (rv[(size_t)b * rstride + c] + y) * 0.5f;
-        ov[(size_t)b * vstride + c] = y;
+    int bb = b0, cc = c0;
+    if (EPT > 0) {
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            if (threadIdx.x + k * kThreads < n) {
+                float y = fmaxf(fmaf(xr[k], scale, shift), 0.f);
+                if (rv) y = (rv[(size_t)bb * rstride + cc] + y) * 0.5f;
+                ov[(size_t)bb * vstride + cc] = y;
+            }
+            bb += sb, cc += sc;
+            if (cc >= a.C) cc -= a.C, ++bb;
+        }
+    } else {
+        for (int i = threadIdx.x; i < n; i += kThreads) {
+            float y = fmaxf(fmaf(xv[(size_t)bb * vstride + cc], scale, shift), 0.f);
+            if (rv) y = (rv[(size_t)bb * rstride + cc] + y) * 0.5f;
+            ov[(size_t)bb * vstride + cc] = y;
+            bb += sb, cc += sc;
+            if (cc >= a.C) cc -= a.C, ++bb;
+        }
     }
 }
 
@@ -102,6 +156,7 @@ struct BwdArgs {
     int B, V, C, training, has_res;
 };
 
+template <int EPT>
 __global__ void __launch_bounds__(kThreads) bwd_kernel(const BwdArgs a)
 {
     __shared__ float sh[kThreads / 32];
@@ -113,14 +168,39 @@ __global__ void __launch_bounds__(kThreads) bwd_kernel(const BwdArgs a)
     const float g = a.gamma ? a.gamma[v] : 1.f, bt = a.beta ? a.beta[v] : 0.f;
     const float half = a.has_res ? 0.5f : 1.0f;
     const float scale = g * invstd, shift = fmaf(-mean, scale, bt);  // the forward's own expression decides the ReLU mask
+    const int sb = kThreads / a.C, sc = kThreads % a.C;
+    const int b0 = threadIdx.x / a.C, c0 = threadIdx.x % a.C;
+    constexpr int R = EPT > 0 ? EPT : 1;
+    float xr[R], dr[R];
     float sdy = 0.f, sdyx = 0.f;
-    for (int i = threadIdx.x; i < n; i += kThreads) {
-        const size_t o = base + (size_t)(i / a.C) * vstride + (i % a.C);
-        const float xv = a.x[o];
-        const float xh = (xv - mean) * invstd;
-        const float dy = fmaf(xv, scale, shift) > 0.f ? a.dout[o] * half : 0.f;
-        sdy += dy;
-        sdyx = fmaf(dy, xh, sdyx);
+    {
+        int bb = b0, cc = c0;
+        if (EPT > 0) {
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                const bool in = threadIdx.x + k * kThreads < n;
+                const size_t o = base + (size_t)bb * vstride + cc;
+                xr[k] = in ? a.x[o] : 0.f;
+                dr[k] = in ? a.dout[o] : 0.f;
+                const float xh = (xr[k] - mean) * invstd;
+                const float dy = (in && fmaf(xr[k], scale, shift) > 0.f) ? dr[k] * half : 0.f;
+                sdy += dy;
+                sdyx = fmaf(dy, xh, sdyx);
+                bb += sb, cc += sc;
+                if (cc >= a.C) cc -= a.C, ++bb;
+            }
+        } else {
+            for (int i = threadIdx.x; i < n; i += kThreads) {
+                const size_t o = base + (size_t)bb * vstride + cc;
+                const float xv = a.x[o];
+                const float xh = (xv - mean) * invstd;
+                const float dy = fmaf(xv, scale, shift) > 0.f ? a.dout[o] * half : 0.f;
+                sdy += dy;
+                sdyx = fmaf(dy, xh, sdyx);
+                bb += sb, cc += sc;
+                if (cc >= a.C) cc -= a.C, ++bb;
+            }
+        }
     }
     sdy = block_sum(sdy, sh);
     sdyx = block_sum(sdyx, sh);
@@ -131,15 +211,43 @@ __global__ void __launch_bounds__(kThreads) bwd_kernel(const BwdArgs a)
     const float inv_n = 1.f / (float)n;
     const float k1 = a.training ? sdy * inv_n : 0.f, k2 = a.training ? sdyx * inv_n : 0.f;
     const float gi = g * invstd;
-    for (int i = threadIdx.x; i < n; i += kThreads) {
-        const size_t o = base + (size_t)(i / a.C) * vstride + (i % a.C);
-        const float xv = a.x[o];
-        const float xh = (xv - mean) * invstd;
-        const float d = a.dout[o];
-        const float dy = fmaf(xv, scale, shift) > 0.f ? d * half : 0.f;
-        a.dx[o] = gi * (dy - k1 - xh * k2);
-        if (a.dres) a.dres[o] = d * 0.5f;
+    int bb = b0, cc = c0;
+    if (EPT > 0) {
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            if (threadIdx.x + k * kThreads < n) {
+                const size_t o = base + (size_t)bb * vstride + cc;
+                const float xh = (xr[k] - mean) * invstd;
+                const float dy = fmaf(xr[k], scale, shift) > 0.f ? dr[k] * half : 0.f;
+                a.dx[o] = gi * (dy - k1 - xh * k2);
+                if (a.dres) a.dres[o] = dr[k] * 0.5f;
+            }
+            bb += sb, cc += sc;
+            if (cc >= a.C) cc -= a.C, ++bb;
+        }
+    } else {
+        for (int i = threadIdx.x; i < n; i += kThreads) {
+            const size_t o = base + (size_t)bb * vstride + cc;
+            const float xv = a.x[o];
+            const float xh = (xv - mean) * invstd;
+            const float d = a.dout[o];
+            const float dy = fmaf(xv, scale, shift) > 0.f ? d * half : 0.f;
+            a.dx[o] = gi * (dy - k1 - xh * k2);
+            if (a.dres) a.dres[o] = d * 0.5f;
+            bb += sb, cc += sc;
+            if (cc >= a.C) cc -= a.C, ++bb;
+        }
     }
+}
+
+template <class Args, class F4, class F8, class F16, class F32, class F0>
+static void dispatch_ept(long long n, F4 f4, F8 f8, F16 f16, F32 f32, F0 f0)
+{
+    if (n <= 4 * kThreads) f4();
+    else if (n <= 8 * kThreads) f8();
+    else if (n <= 16 * kThreads) f16();
+    else if (n <= 32 * kThreads) f32();
+    else f0();
 }
 
 }  // namespace bn
@@ -162,7 +270,11 @@ extern "C" int geom_bn_relu_res_fwd(int b, int V, int C, const float *x, const f
     cudaStream_t st = (cudaStream_t)stream;
     {
         prof::Scope ps(st, prof::kBnFwd);
-        bn::fwd_kernel<<<V, bn::kThreads, 0, st>>>(a);
+        bn::dispatch_ept<bn::FwdArgs>((long long)b * C, [&] { bn::fwd_kernel<4><<<V, bn::kThreads, 0, st>>>(a); },
+                                      [&] { bn::fwd_kernel<8><<<V, bn::kThreads, 0, st>>>(a); },
+                                      [&] { bn::fwd_kernel<16><<<V, bn::kThreads, 0, st>>>(a); },
+                                      [&] { bn::fwd_kernel<32><<<V, bn::kThreads, 0, st>>>(a); },
+                                      [&] { bn::fwd_kernel<0><<<V, bn::kThreads, 0, st>>>(a); });
     }
     return status_from_cuda(cudaGetLastError());
 }
@@ -182,7 +294,11 @@ extern "C" int geom_bn_relu_res_bwd(int b, int V, int C, const float *x, const f
     cudaStream_t st = (cudaStream_t)stream;
     {
         prof::Scope ps(st, prof::kBnBwd);
-        bn::bwd_kernel<<<V, bn::kThreads, 0, st>>>(a);
+        bn::dispatch_ept<bn::BwdArgs>((long long)b * C, [&] { bn::bwd_kernel<4><<<V, bn::kThreads, 0, st>>>(a); },
+                                      [&] { bn::bwd_kernel<8><<<V, bn::kThreads, 0, st>>>(a); },
+                                      [&] { bn::bwd_kernel<16><<<V, bn::kThreads, 0, st>>>(a); },
+                                      [&] { bn::bwd_kernel<32><<<V, bn::kThreads, 0, st>>>(a); },
+                                      [&] { bn::bwd_kernel<0><<<V, bn::kThreads, 0, st>>>(a); });
     }
     return status_from_cuda(cudaGetLastError());
 }

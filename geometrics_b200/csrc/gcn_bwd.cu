@@ -48,43 +48,91 @@ __global__ void __launch_bounds__(256) transpose_kernel(int R, int C, const floa
     }
 }
 
-// dW[k][n] += sum over this CTA's slice of m of X[m][k] * dS[m][n]: 64 x 64 output tile, 4 x 4 per thread, 16 rows of m per
-// shared-memory step; the partial tiles of the M slices meet in fp32 atomics (dW zeroed by the entry point).
-constexpr int TK = 64, TN = 64, TM = 16;
+// dW partial: P[slice][k][n] = sum over the slice's rows m of X[m][k] * dS[m][n].  128 (k) x 64 (n) output tile per CTA,
+// 8 x 4 per thread (256 threads), 8 rows of m per shared-memory step; a second kernel adds the slices in a fixed order
+// (deterministic, no atomics).
+constexpr int TK = 128, TN = 64, TM = 8;
 __global__ void __launch_bounds__(256) gemm_tn_kernel(int M, int K, int N, const float *__restrict__ X, const float *__restrict__ dS,
-                                                      float *__restrict__ dW, int rows_per_slice)
+                                                      float *__restrict__ P, int rows_per_slice)
 {
-    __shared__ __align__(16) float sx[TM][TK + 4], sd[TM][TN + 4];
+    __shared__ __align__(16) float sx[2][TM][TK], sd[2][TM][TN];
     const int k0 = blockIdx.x * TK, n0 = blockIdx.y * TN;
     const int m_begin = blockIdx.z * rows_per_slice, m_end = min(M, m_begin + rows_per_slice);
-    const int tk = (threadIdx.x >> 4) * 4, tn = (threadIdx.x & 15) * 4;
-    float acc[4][4] = {};
-    for (int m0 = m_begin; m0 < m_end; m0 += TM) {
-        // 16 x 64 of each operand: 1024 floats, 4 per thread, coalesced along the row
-        for (int e = threadIdx.x; e < TM * TK; e += 256) {
-            const int r = e / TK, c = e % TK;
-            const int m = m0 + r;
-            sx[r][c] = (m < m_end && k0 + c < K) ? X[(size_t)m * K + k0 + c] : 0.f;
-            sd[r][c] = (m < m_end && n0 + c < N) ? dS[(size_t)m * N + n0 + c] : 0.f;
+    const int tk = (threadIdx.x >> 4) * 8, tn = (threadIdx.x & 15) * 4;
+    // staging: thread t copies X[m0 + t/32][k0 + (t%32)*4 .. +3] and dS[m0 + t/16 (first 128 threads)][n0 + (t%16)*4 .. +3]
+    const int xr = threadIdx.x >> 5, xc = (threadIdx.x & 31) * 4;
+    const int dr = (threadIdx.x & 127) >> 4, dc = (threadIdx.x & 15) * 4;
+    const bool vec = (K % 4 == 0) && (N % 4 == 0);
+    auto load_x = [&](int m0) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int m = m0 + xr;
+        if (m < m_end) {
+            const float *p = X + (size_t)m * K + k0 + xc;
+            if (vec && k0 + xc + 3 < K) v = *reinterpret_cast<const float4 *>(p);
+            else {
+                if (k0 + xc < K) v.x = p[0];
+                if (k0 + xc + 1 < K) v.y = p[1];
+                if (k0 + xc + 2 < K) v.z = p[2];
+                if (k0 + xc + 3 < K) v.w = p[3];
+            }
         }
+        return v;
+    };
+    auto load_d = [&](int m0) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int m = m0 + dr;
+        if (threadIdx.x < 128 && m < m_end) {
+            const float *p = dS + (size_t)m * N + n0 + dc;
+            if (vec && n0 + dc + 3 < N) v = *reinterpret_cast<const float4 *>(p);
+            else {
+                if (n0 + dc < N) v.x = p[0];
+                if (n0 + dc + 1 < N) v.y = p[1];
+                if (n0 + dc + 2 < N) v.z = p[2];
+                if (n0 + dc + 3 < N) v.w = p[3];
+            }
+        }
+        return v;
+    };
+    float acc[8][4] = {};
+    float4 vx = load_x(m_begin), vd = load_d(m_begin);
+    int buf = 0;
+    for (int m0 = m_begin; m0 < m_end; m0 += TM) {
+        *reinterpret_cast<float4 *>(&sx[buf][xr][xc]) = vx;
+        if (threadIdx.x < 128) *reinterpret_cast<float4 *>(&sd[buf][dr][dc]) = vd;
         __syncthreads();
+        if (m0 + TM < m_end) {  // next step's operands travel while this one is multiplied
+            vx = load_x(m0 + TM);
+            vd = load_d(m0 + TM);
+        }
 #pragma unroll
         for (int r = 0; r < TM; ++r) {
-            const float4 xa = *reinterpret_cast<const float4 *>(&sx[r][tk]);
-            const float4 da = *reinterpret_cast<const float4 *>(&sd[r][tn]);
-            const float xs[4] = {xa.x, xa.y, xa.z, xa.w}, ds[4] = {da.x, da.y, da.z, da.w};
+            const float4 xa = *reinterpret_cast<const float4 *>(&sx[buf][r][tk]);
+            const float4 xb = *reinterpret_cast<const float4 *>(&sx[buf][r][tk + 4]);
+            const float4 da = *reinterpret_cast<const float4 *>(&sd[buf][r][tn]);
+            const float xs[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w}, ds[4] = {da.x, da.y, da.z, da.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 8; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xs[i], ds[j], acc[i][j]);
         }
-        __syncthreads();
+        buf ^= 1;  // two buffers: the next store cannot overtake this step's reads (one barrier per step)
     }
+    float *out = P + (size_t)blockIdx.z * K * N;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-            if (k0 + tk + i < K && n0 + tn + j < N) atomicAdd(dW + (size_t)(k0 + tk + i) * N + n0 + tn + j, acc[i][j]);
+            if (k0 + tk + i < K && n0 + tn + j < N) out[(size_t)(k0 + tk + i) * N + n0 + tn + j] = acc[i][j];
+}
+
+// dW[e] = sum over slices of P[slice][e], slices in ascending order
+__global__ void __launch_bounds__(256) slice_sum_kernel(int slices, long long elems, const float *__restrict__ P, float *__restrict__ dW)
+{
+    const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (e >= elems) return;
+    float s = 0.f;
+    for (int z = 0; z < slices; ++z) s += P[(size_t)z * elems + e];
+    dW[e] = s;
 }
 
 }  // namespace gcn_bwd
@@ -93,13 +141,15 @@ __global__ void __launch_bounds__(256) gemm_tn_kernel(int M, int K, int N, const
 using namespace geom;
 
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+constexpr int kMaxSlices = 32;  // M slices of the dW GEMM
 
 extern "C" size_t geom_zeron_gcn_bwd_workspace_bytes(int b, int V, int in_features, int out_features)
 {
     if (b < 0 || V < 0 || in_features < 0 || out_features < 0) return 0;
     const size_t M = (size_t)b * V;
-    // dS | W^T | workspace of the dX GEMM (out -> in features, nothing smoothed)
+    // dS | W^T | dW slice partials | workspace of the dX GEMM (out -> in features, nothing smoothed)
     return align256(M * out_features * 4) + align256((size_t)in_features * out_features * 4) +
+           align256((size_t)kMaxSlices * in_features * out_features * 4) +
            geom_zeron_gcn_tensor_workspace_bytes(b, V, out_features, in_features, 0) + 256;
 }
 
@@ -118,7 +168,8 @@ extern "C" int geom_zeron_gcn_bwd(int b, int V, int in_features, int out_feature
     char *w = (char *)workspace;
     float *dS = (float *)w;
     float *Wt = (float *)(w + align256((size_t)M * out_features * 4));
-    void *gemm_ws = (char *)Wt + align256((size_t)in_features * out_features * 4);
+    float *P = (float *)((char *)Wt + align256((size_t)in_features * out_features * 4));
+    void *gemm_ws = (char *)P + align256((size_t)kMaxSlices * in_features * out_features * 4);
     const size_t gemm_ws_bytes = workspace_bytes - (size_t)((char *)gemm_ws - w);
     int rc = GEOM_OK;
     cudaError_t e = cudaSuccess;
@@ -135,17 +186,18 @@ extern "C" int geom_zeron_gcn_bwd(int b, int V, int in_features, int out_feature
         dSp = dS;
     }
     if (dW) {
-        if ((e = cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)in_features * out_features, st)) != cudaSuccess) return status_from_cuda(e);
         int dev = 0, sms = 148;
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const int tiles = ((in_features + gcn_bwd::TK - 1) / gcn_bwd::TK) * ((out_features + gcn_bwd::TN - 1) / gcn_bwd::TN);
-        int slices = std::max(1, (3 * sms + tiles - 1) / tiles);                        // ~3 CTAs per SM
-        slices = (int)std::min<long long>(slices, (M + 4 * gcn_bwd::TM - 1) / (4 * gcn_bwd::TM));  // >= 64 rows per slice
+        int slices = std::max(1, (2 * sms + tiles - 1) / tiles);                                  // ~2 CTAs per SM
+        slices = (int)std::min<long long>(std::min(slices, kMaxSlices), (M + 63) / 64);           // >= 64 rows per slice
         const int rows = (int)((((M + slices - 1) / slices) + gcn_bwd::TM - 1) / gcn_bwd::TM * gcn_bwd::TM);
+        slices = (int)((M + rows - 1) / rows);
+        const long long elems = (long long)in_features * out_features;
         prof::Scope ps(st, prof::kGcnBwdGemm);
-        gcn_bwd::gemm_tn_kernel<<<dim3((in_features + gcn_bwd::TK - 1) / gcn_bwd::TK, (out_features + gcn_bwd::TN - 1) / gcn_bwd::TN,
-                                       (unsigned)((M + rows - 1) / rows)),
-                                  256, 0, st>>>((int)M, in_features, out_features, X, dSp, dW, rows);
+        gcn_bwd::gemm_tn_kernel<<<dim3((in_features + gcn_bwd::TK - 1) / gcn_bwd::TK, (out_features + gcn_bwd::TN - 1) / gcn_bwd::TN, slices),
+                                  256, 0, st>>>((int)M, in_features, out_features, X, dSp, P, rows);
+        gcn_bwd::slice_sum_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, st>>>(slices, elems, P, dW);
     }
     if (dX) {
         gcn_bwd::transpose_kernel<<<dim3((out_features + 31) / 32, (in_features + 31) / 32), 256, 0, st>>>(in_features, out_features, W, Wt);

@@ -61,7 +61,7 @@ def csr_from_dense(adj: torch.Tensor) -> CsrAdjacency:
             return cached
         del _csr_cache[key]
     a = adj.detach().contiguous()
-    with torch.cuda.device(a.device):
+    with _lib.on_device(a.device):
         c = CsrAdjacency()
         c.V = a.shape[0]
         c.nnz, c.row_ptr, c.col_idx, c.val = _build_csr(a, False)
@@ -81,7 +81,7 @@ class CsrMatmulFunction(torch.autograd.Function):
         xc = x.detach().contiguous()
         b, v, c = xc.shape
         y = torch.empty_like(xc)
-        with torch.cuda.device(xc.device):
+        with _lib.on_device(xc.device):
             _lib.check(L.geom_csr_spmm(b, v, c, csr.row_ptr.data_ptr(), csr.col_idx.data_ptr(), csr.val.data_ptr(),
                                        xc.data_ptr(), y.data_ptr(), _lib.current_stream_ptr(xc.device)), "geom_csr_spmm")
         ctx.csr = csr
@@ -94,7 +94,7 @@ class CsrMatmulFunction(torch.autograd.Function):
         dy = dy.contiguous()
         b, v, c = dy.shape
         dx = torch.empty_like(dy)
-        with torch.cuda.device(dy.device):
+        with _lib.on_device(dy.device):
             _lib.check(L.geom_csr_spmm(b, v, c, csr.t_row_ptr.data_ptr(), csr.t_col_idx.data_ptr(), csr.t_val.data_ptr(),
                                        dy.data_ptr(), dx.data_ptr(), _lib.current_stream_ptr(dy.device)), "geom_csr_spmm")
         return dx, None
@@ -127,7 +127,7 @@ class ZeroNGCNFunction(torch.autograd.Function):
         b, v, fin = xc.shape
         fout = wc.shape[1]
         dev = xc.device
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             y = torch.empty((b, v, fout), dtype=torch.float32, device=dev)
             wsb = (L.geom_zeron_gcn_tensor_workspace_bytes(b, v, fin, fout, ksplit) if tensor
                    else L.geom_zeron_gcn_workspace_bytes(b, v, ksplit))
@@ -153,7 +153,7 @@ class ZeroNGCNFunction(torch.autograd.Function):
         fin = xc.shape[2]
         dev = dy.device
         need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             dx = torch.empty_like(xc) if need_x else None
             dw = torch.empty_like(wc) if need_w else None
             db = torch.empty(fout, dtype=torch.float32, device=dev) if need_b else None
@@ -183,7 +183,7 @@ class BnReluResFunction(torch.autograd.Function):
             if res.shape != xc.shape or res.stride(2) != 1 or res.stride(0) != v * res.stride(1):
                 res = res.contiguous()
             ld_res = res.stride(1)
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             out = torch.empty_like(xc)
             stats = torch.empty(2, v, dtype=torch.float32, device=dev)
             ptr = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
@@ -203,7 +203,7 @@ class BnReluResFunction(torch.autograd.Function):
         b, v, c = xc.shape
         dev = xc.device
         need_res = ctx.has_res and ctx.needs_input_grad[1]
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             dx = torch.empty_like(xc)
             dres = torch.empty_like(xc) if need_res else None
             dg = torch.empty(v, dtype=torch.float32, device=dev) if gamma is not None else None
@@ -213,6 +213,110 @@ class BnReluResFunction(torch.autograd.Function):
                                               stats[1].data_ptr(), int(ctx.training), int(ctx.has_res), dx.data_ptr(), ptr(dres),
                                               ptr(dg), ptr(dbt), _lib.current_stream_ptr(dev)), "geom_bn_relu_res_bwd")
         return dx, dres, dg, dbt, None, None, None, None, None, None
+
+
+_ws_cache: dict = {}
+
+
+def _workspace(dev, nbytes: int, slot: str):
+    """A reusable scratch buffer per (device, slot): the kernels only need it for the duration of the call they are
+    enqueued by and every user runs on the current stream, so stream order makes reuse safe (a per-call torch.empty costs
+    a few microseconds of host time, tens of times per deformation block)."""
+    key = (dev.index, slot, torch.cuda.current_stream(dev).cuda_stream)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() * 4 < nbytes:
+        buf = _ws_cache[key] = torch.empty(max(nbytes // 4 + 64, 1024), dtype=torch.float32, device=dev)
+    return buf
+
+
+class GcnBnStageFunction(torch.autograd.Function):
+    """One stage of BatchMeshDeformationBlock (models.py:241-294) as ONE autograd node:
+        y = [adj . (xW)[:, :k] | (xW)[:, k:]] + b;   out = relu(BatchNorm1d_V(y))  [; out = (res + out) / 2]
+    forward = geom_zeron_gcn_fwd + geom_bn_relu_res_fwd, backward = geom_bn_relu_res_bwd + geom_zeron_gcn_bwd.  The same
+    kernels as ZeroNGCNFunction / BnReluResFunction; merging the nodes halves the host-side cost of the block, which is
+    launch-bound at the reference's shapes (B=16, V=482)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, gamma, beta, res, csr, ksplit, tensor, running_mean, running_var, batches_tracked,
+                training, momentum, eps):
+        L = _lib.lib()
+        xc, wc = x.detach().contiguous(), weight.detach().contiguous()
+        b, v, fin = xc.shape
+        fout = wc.shape[1]
+        dev = xc.device
+        ld_res = 0
+        if res is not None:
+            if res.shape != (b, v, fout) or res.stride(2) != 1 or res.stride(0) != v * res.stride(1):
+                res = res.contiguous()
+            ld_res = res.stride(1)
+        ptr = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
+        with _lib.on_device(dev):
+            sp = _lib.current_stream_ptr(dev)
+            y = torch.empty((b, v, fout), dtype=torch.float32, device=dev)
+            out = torch.empty_like(y)
+            stats = torch.empty(2, v, dtype=torch.float32, device=dev)
+            wsb = (L.geom_zeron_gcn_tensor_workspace_bytes(b, v, fin, fout, ksplit) if tensor
+                   else L.geom_zeron_gcn_workspace_bytes(b, v, ksplit))
+            ws = _workspace(dev, wsb, "gcn_fwd")
+            _lib.check(L.geom_zeron_gcn_fwd(b, v, fin, fout, ksplit, xc.data_ptr(), wc.data_ptr(), ptr(bias), csr.row_ptr.data_ptr(),
+                                            csr.col_idx.data_ptr(), csr.val.data_ptr(), y.data_ptr(), 2 if tensor else 0,
+                                            ws.data_ptr(), ws.numel() * 4, sp), "geom_zeron_gcn_fwd")
+            _lib.check(L.geom_bn_relu_res_fwd(b, v, fout, y.data_ptr(), ptr(res), ld_res, ptr(gamma), ptr(beta), ptr(running_mean),
+                                              ptr(running_var), ptr(batches_tracked), int(training), float(momentum), float(eps),
+                                              stats[0].data_ptr(), stats[1].data_ptr(), out.data_ptr(), sp), "geom_bn_relu_res_fwd")
+        ctx.save_for_backward(xc, wc, y, gamma, beta, stats)
+        ctx.csr, ctx.ksplit, ctx.tensor, ctx.has_bias = csr, ksplit, bool(tensor), bias is not None
+        ctx.training, ctx.has_res = bool(training), res is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        xc, wc, y, gamma, beta, stats = ctx.saved_tensors
+        csr, ksplit = ctx.csr, ctx.ksplit
+        L = _lib.lib()
+        dout = dout.contiguous()
+        b, v, fin = xc.shape
+        fout = wc.shape[1]
+        dev = xc.device
+        need_x, need_w, need_b, need_res = (ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2],
+                                            ctx.has_res and ctx.needs_input_grad[5])
+        ptr = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
+        with _lib.on_device(dev):
+            sp = _lib.current_stream_ptr(dev)
+            dy = torch.empty_like(y)
+            dres = torch.empty_like(y) if need_res else None
+            dg = torch.empty(v, dtype=torch.float32, device=dev) if gamma is not None else None
+            dbt = torch.empty(v, dtype=torch.float32, device=dev) if beta is not None else None
+            _lib.check(L.geom_bn_relu_res_bwd(b, v, fout, y.data_ptr(), dout.data_ptr(), ptr(gamma), ptr(beta), stats[0].data_ptr(),
+                                              stats[1].data_ptr(), int(ctx.training), int(ctx.has_res), dy.data_ptr(), ptr(dres),
+                                              ptr(dg), ptr(dbt), sp), "geom_bn_relu_res_bwd")
+            dx = torch.empty_like(xc) if need_x else None
+            dw = torch.empty_like(wc) if need_w else None
+            db = torch.empty(fout, dtype=torch.float32, device=dev) if need_b else None
+            ws = _workspace(dev, L.geom_zeron_gcn_bwd_workspace_bytes(b, v, fin, fout), "gcn_bwd")
+            _lib.check(L.geom_zeron_gcn_bwd(b, v, fin, fout, ksplit, xc.data_ptr(), wc.data_ptr(), dy.data_ptr(),
+                                            csr.t_row_ptr.data_ptr(), csr.t_col_idx.data_ptr(), csr.t_val.data_ptr(), ptr(dx), ptr(dw),
+                                            ptr(db), 2 if ctx.tensor else 0, ws.data_ptr(), ws.numel() * 4, sp), "geom_zeron_gcn_bwd")
+        return dx, dw, db, dg, dbt, dres, None, None, None, None, None, None, None, None, None
+
+
+def gcn_bn_stage(x, layer, bn: nn.BatchNorm1d, csr, res=None, tensor=None):
+    """``F.relu(bn(layer(x, adj, identity)))`` [then ``(res + .) / 2``] for a Batch_Image_ZERON_GCNGCN ``layer`` and
+    ``bn = nn.BatchNorm1d(V)`` as one autograd node (see GcnBnStageFunction); BatchNorm semantics as in bn_relu_res."""
+    _lib.require_cuda_f32("input", x, None)
+    weight = layer.weight1[0] if layer.weight1.dim() == 3 else layer.weight1
+    if x.dim() != 3 or x.shape[1] != bn.num_features or x.shape[1] != csr.V or x.shape[2] != weight.shape[0]:
+        raise ValueError(f"input {tuple(x.shape)} does not fit layer {tuple(weight.shape)} / BatchNorm1d({bn.num_features}) / adjacency {csr.V}")
+    use_batch = bn.training or bn.running_mean is None
+    momentum = bn.momentum
+    if momentum is None:
+        momentum = 1.0 / float(int(bn.num_batches_tracked) + 1) if bn.num_batches_tracked is not None else 0.0
+    track = bn.training and bn.track_running_stats
+    keep = track or not use_batch
+    return GcnBnStageFunction.apply(x, weight, layer.bias, bn.weight, bn.bias, res, csr, weight.shape[1] // layer.split,
+                                    TENSOR_GEMM if tensor is None else bool(tensor), bn.running_mean if keep else None,
+                                    bn.running_var if keep else None, bn.num_batches_tracked if track else None, use_batch,
+                                    momentum, bn.eps)
 
 
 def bn_relu_res(x, bn: nn.BatchNorm1d, res=None):

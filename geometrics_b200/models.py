@@ -11,7 +11,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from .layers import (BatchGCNMax, BatchZERON_GCN, Batch_Image_ZERON_GCNGCN, GCNMax, Image_ZERON_GCNGCN,
-                     ZERON_GCN, bn_relu_res, csr_from_dense)
+                     ZERON_GCN, bn_relu_res, csr_from_dense, gcn_bn_stage)
 
 _identity = None  # activation=None means identity in layers.zeron_gcn
 
@@ -60,11 +60,14 @@ class BatchMeshDeformationBlock(_DeformationStack):
         for i in range(1, 15):
             setattr(self, f"bn{i}", nn.BatchNorm1d(verts))
 
-    FUSED_BN = True  # BatchNorm1d(V) + ReLU + residual average in one kernel (bn.cu); False: the torch modules
+    FUSED_BN = True     # BatchNorm1d(V) + ReLU + residual average in one kernel (bn.cu); False: the torch modules
+    FUSED_STAGE = True  # ... and layer + normalisation as ONE autograd node (layers.GcnBnStageFunction)
 
     def _gcn(self, i, x, adj, res=None):
-        x = getattr(self, f"gc{i}")(x, adj, _identity)
         bn = getattr(self, f"bn{i}")
+        if self.FUSED_BN and self.FUSED_STAGE and x.is_cuda and x.dim() == 3:
+            return gcn_bn_stage(x, getattr(self, f"gc{i}"), bn, adj, res)
+        x = getattr(self, f"gc{i}")(x, adj, _identity)
         if self.FUSED_BN and x.is_cuda and x.dim() == 3:
             return bn_relu_res(x, bn, res)
         x = F.relu(bn(x))

@@ -29,7 +29,7 @@ def tri_forward(xyz1, tri1, tri2, tri3, *, exact_tail: bool = False, want_dist: 
     b, n, _ = xyz1.shape
     m = tri1.shape[1]
     dev = xyz1.device
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         dist = torch.empty((b, n), dtype=torch.float32, device=dev) if want_dist else None
         point = torch.empty((b, n), dtype=torch.int32, device=dev)
         index = torch.empty((b, n), dtype=torch.int32, device=dev)

@@ -71,7 +71,7 @@ def face_areas(verts: torch.Tensor, faces: torch.Tensor, normalise: bool = True)
     faces = _faces_i64(faces, verts.device)
     b, v, _ = verts.shape
     f = faces.shape[0]
-    with torch.cuda.device(verts.device):
+    with _lib.on_device(verts.device):
         areas = torch.empty((b, f), dtype=torch.float32, device=verts.device)
         _lib.check(L.geom_face_areas(b, v, verts.data_ptr(), f, faces.data_ptr(), areas.data_ptr(),
                                      1 if normalise else 0, _lib.current_stream_ptr(verts.device)), "geom_face_areas")
@@ -89,7 +89,7 @@ class SampleFunction(torch.autograd.Function):
         b, v, _ = vc.shape
         num = choices.numel() // max(b, 1)
         dev = vc.device
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             points = torch.empty((b, num, 3), dtype=torch.float32, device=dev)
             _lib.check(L.geom_sample_fwd(b, v, vc.data_ptr(), faces.shape[0], faces.data_ptr(), num,
                                          choices.data_ptr(), r1.data_ptr(), r2.data_ptr(), points.data_ptr(),
@@ -105,7 +105,7 @@ class SampleFunction(torch.autograd.Function):
         L = _lib.lib()
         g = grad_points.contiguous()
         dev = g.device
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             gv = torch.empty((b, v, 3), dtype=torch.float32, device=dev)
             _lib.check(L.geom_sample_bwd(b, v, faces.shape[0], faces.data_ptr(), num, choices.data_ptr(),
                                          r1.data_ptr(), r2.data_ptr(), g.data_ptr(), gv.data_ptr(),
@@ -200,7 +200,7 @@ class ChamferLossFunction(torch.autograd.Function):
         b, n, _ = a.shape
         m = c.shape[1]
         dev = a.device
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             sums = torch.empty(2, dtype=torch.float32, device=dev)
             wsb = L.geom_chamfer_loss_workspace_bytes(b, n, m)
             ws = torch.empty(max(wsb // 16, 1) * 2, dtype=torch.float64, device=dev)
@@ -229,7 +229,7 @@ class ChamferLossFunction(torch.autograd.Function):
         dev = a.device
         w = grad_sums.to(torch.float32).contiguous()
         need1, need2 = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             g1 = torch.empty_like(a) if need1 else None
             g2 = torch.empty_like(c) if need2 else None
             _lib.check(L.geom_chamfer_loss_bwd(b, n, a.data_ptr(), m, c.data_ptr(), idx1.data_ptr(), idx2.data_ptr(),
@@ -300,7 +300,7 @@ class TriLossFunction(torch.autograd.Function):
         p, v = gt_points.detach().contiguous(), verts.detach().contiguous()
         b, n, _ = p.shape
         dev = p.device
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             total = torch.empty(1, dtype=torch.float32, device=dev)
             wsb = L.geom_tri_loss_workspace_bytes(b, n)
             ws = torch.empty(max(wsb // 8, 1), dtype=torch.float64, device=dev)
@@ -318,7 +318,7 @@ class TriLossFunction(torch.autograd.Function):
         b, n, _ = p.shape
         dev = p.device
         w = grad_total.to(torch.float32).contiguous()
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             gv = torch.empty_like(v)
             _lib.check(L.geom_tri_loss_bwd(b, n, p.data_ptr(), v.shape[1], v.data_ptr(), faces.shape[0],
                                            faces.data_ptr(), option.data_ptr(), index.data_ptr(), w.data_ptr(),
@@ -368,7 +368,7 @@ class EdgeLossFunction(torch.autograd.Function):
         b, v, _ = vc.shape
         f = faces.shape[0]
         dev = vc.device
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             acc = torch.empty(1, dtype=torch.float64, device=dev)
             _lib.check(L.geom_edge_loss_fwd(b, v, vc.data_ptr(), f, faces.data_ptr(), acc.data_ptr(),
                                             _lib.current_stream_ptr(dev)), "geom_edge_loss_fwd")
@@ -383,7 +383,7 @@ class EdgeLossFunction(torch.autograd.Function):
         b, v, _ = vc.shape
         dev = vc.device
         gc = g.detach().to(torch.float32).contiguous()
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             gv = torch.empty_like(vc)
             _lib.check(L.geom_edge_loss_bwd(b, v, vc.data_ptr(), faces.shape[0], faces.data_ptr(), gc.data_ptr(), ctx.scale,
                                             gv.data_ptr(), _lib.current_stream_ptr(dev)), "geom_edge_loss_bwd")
@@ -465,7 +465,7 @@ class ProjectFunction(torch.autograd.Function):
         vc, ic = verts.detach().contiguous(), img_info.detach().contiguous()
         b, v, _ = vc.shape
         dev = vc.device
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             xs = torch.empty((b, v), dtype=torch.float32, device=dev)
             ys = torch.empty((b, v), dtype=torch.float32, device=dev)
             _lib.check(L.geom_project_fwd(b, v, vc.data_ptr(), ic.data_ptr(), xs.data_ptr(), ys.data_ptr(),
@@ -481,7 +481,7 @@ class ProjectFunction(torch.autograd.Function):
         dev = vc.device
         gxs = gxs.contiguous() if gxs is not None else None
         gys = gys.contiguous() if gys is not None else None
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             gv = torch.empty_like(vc)
             _lib.check(L.geom_project_bwd(b, v, vc.data_ptr(), ic.data_ptr(), gxs.data_ptr() if gxs is not None else None,
                                           gys.data_ptr() if gys is not None else None, gv.data_ptr(),
@@ -524,7 +524,7 @@ class PoolFunction(torch.autograd.Function):
         chans = [int(m.shape[1]) for m in maps]
         dims = [int(m.shape[-1]) for m in maps]
         total = sum(chans)
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             out = out_buf if out_buf is not None else torch.empty((b, v, total), dtype=torch.float32, device=dev)
             ptrs = (C.c_void_p * len(maps))(*[m.data_ptr() for m in maps])
             ch = (C.c_int * len(maps))(*chans)
@@ -548,7 +548,7 @@ class PoolFunction(torch.autograd.Function):
         dev = xs.device
         dout = dout.contiguous()
         want_maps = [ctx.needs_input_grad[4 + k] for k in range(len(maps))]
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             gmaps = [torch.zeros_like(m) if w else None for m, w in zip(maps, want_maps)]
             gxs = torch.empty_like(xs) if ctx.needs_input_grad[0] else None
             gys = torch.empty_like(ys) if ctx.needs_input_grad[1] else None

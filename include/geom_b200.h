@@ -305,8 +305,8 @@ GEOM_API int geom_zeron_gcn_bwd_smooth(int b, int V, int out_features, int kspli
 /* Whole backward of the layer (autograd of layers.py:107-116), every GEMM in this library:
  *   dS = [adj^T . dY[:, :ksplit] | dY[:, ksplit:]],  db = column sums of dY,  dW = X^T dS,  dX = dS W^T.
  * dX / dW / db may be NULL (not needed).  flags: GEOM_GCN_TENSOR runs dX on the tensor cores when 16 <= in <= 256.
- * workspace >= geom_zeron_gcn_bwd_workspace_bytes, 16-byte aligned.  dW accumulates split-M partial tiles with fp32
- * atomics (summation order varies run to run in the last bits, like cuBLAS split-K). */
+ * workspace >= geom_zeron_gcn_bwd_workspace_bytes, 16-byte aligned.  dW is reduced over M in slices whose partial
+ * tiles are added in a fixed order (deterministic). */
 GEOM_API size_t geom_zeron_gcn_bwd_workspace_bytes(int b, int V, int in_features, int out_features);
 GEOM_API int geom_zeron_gcn_bwd(int b, int V, int in_features, int out_features, int ksplit, const float *X, const float *W,
                        const float *dY, const int *t_row_ptr, const int *t_col_idx, const float *t_val, float *dX,
