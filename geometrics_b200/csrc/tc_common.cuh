@@ -51,6 +51,18 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
                      : "memory");
     }
 }
+// The same wait with a non-blocking probe first: when the phase is already complete (the common case for a consumer that
+// is behind its producer) test_wait answers in one shared-memory round trip, while try_wait costs ~140 cycles even then
+// (profiles/r01_tc_probes.txt).
+__device__ __forceinline__ void mbar_wait_fast(unsigned long long *bar, unsigned parity)
+{
+    unsigned done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    if (!done) mbar_wait(bar, parity);
+}
 __device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
