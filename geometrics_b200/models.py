@@ -65,10 +65,13 @@ class BatchMeshDeformationBlock(_DeformationStack):
 
     def _gcn(self, i, x, adj, res=None):
         bn = getattr(self, f"bn{i}")
-        if self.FUSED_BN and self.FUSED_STAGE and x.is_cuda and x.dim() == 3:
+        # the fused kernels implement nn.BatchNorm1d itself; anything else (e.g. SyncBatchNorm after conversion for
+        # multi-GPU training) keeps its own module semantics
+        fused = self.FUSED_BN and type(bn) is nn.BatchNorm1d and x.is_cuda and x.dim() == 3
+        if fused and self.FUSED_STAGE:
             return gcn_bn_stage(x, getattr(self, f"gc{i}"), bn, adj, res)
         x = getattr(self, f"gc{i}")(x, adj, _identity)
-        if self.FUSED_BN and x.is_cuda and x.dim() == 3:
+        if fused:
             return bn_relu_res(x, bn, res)
         x = F.relu(bn(x))
         return x if res is None else (res + x) / 2

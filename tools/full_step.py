@@ -154,7 +154,7 @@ def main():
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    torch.manual_seed(41 + rank)
+    torch.manual_seed(41)  # identical initial weights on every rank (DDP would broadcast rank 0's anyway)
     from geometrics_b200.sharding import shard_bounds
     lo, hi = shard_bounds(args.batch, rank, world)
     bsz = hi - lo
@@ -185,13 +185,17 @@ def main():
         surface, lap, dense_gcn, dense_adj, note = reference_ops(dev)
         dense_adj[0] = adj_info["adj"]
         g.layers.zeron_gcn = dense_gcn
+        g.BatchMeshDeformationBlock.FUSED_BN = False  # torch BatchNorm1d / relu / add / div, as the reference runs them
 
-    gen = torch.Generator().manual_seed(100 + rank)
-    images = torch.rand(bsz, 4, 224, 224, generator=gen).to(dev)
-    img_info = torch.stack((torch.rand(bsz, generator=gen) * 360, 25 + 5 * torch.rand(bsz, generator=gen),
-                            0.6 + 0.4 * torch.rand(bsz, generator=gen)), dim=1).to(dev)
-    gt = (torch.rand(bsz, args.samples, 3, generator=gen) - 0.5).to(dev)
-    latent = torch.randn(bsz, 50, generator=gen).to(dev)
+    # the GLOBAL batch is generated with one seed and sliced, so that every GPU count trains on the same 32 items
+    gen = torch.Generator().manual_seed(100)
+    gb = args.batch
+    images = torch.rand(gb, 4, 224, 224, generator=gen)[lo:hi].to(dev)
+    img_info = torch.stack((torch.rand(gb, generator=gen) * 360, 25 + 5 * torch.rand(gb, generator=gen),
+                            0.6 + 0.4 * torch.rand(gb, generator=gen)), dim=1)[lo:hi].to(dev)
+    gt = (torch.rand(gb, args.samples, 3, generator=gen) - 0.5)[lo:hi].to(dev)
+    latent = torch.randn(gb, 50, generator=gen)[lo:hi].to(dev)
+    torch.manual_seed(1000 + rank)  # sampler draws differ per rank, as they would in training
 
     def step():
         opt.zero_grad(set_to_none=True)
@@ -221,11 +225,14 @@ def main():
         loss = edge + surf + lap_loss + lat
         loss.backward()
         opt.step()
-        return float(loss), f1
+        return loss.detach(), f1
 
     try:
+        first = None
         for _ in range(args.warmup):
             out = step()
+            if first is None:
+                first = out[0].clone()  # loss of the very first step: same weights and data on every GPU count
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -236,14 +243,19 @@ def main():
         dt = (time.perf_counter() - t0) / args.steps
     finally:
         g.layers.zeron_gcn = orig_gcn
+        g.BatchMeshDeformationBlock.FUSED_BN = True
+    first = first.double().reshape(1)
     if world > 1:
         t = torch.tensor([dt], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t)
+        dist.all_reduce(first)  # equal shards: the global-batch loss is the mean of the per-rank means
+        first /= world
     if rank == 0:
         print(json.dumps({"bench": "full GEOMetrics training step (config 5), synthetic", "impl": args.impl, "hot_path": note,
                           "global_batch": args.batch, "n_gpus": world, "samples": args.samples, "verts": V,
-                          "ms_per_step": dt * 1e3, "steps_per_s": 1 / dt, "loss": out[0], "f1": out[1],
+                          "ms_per_step": dt * 1e3, "steps_per_s": 1 / dt, "loss": float(out[0]), "f1": float(out[1]),
+                          "first_step_loss_global": float(first),
                           "latent": bool(args.latent), "sync_bn": bool(args.sync_bn)}), flush=True)
     if world > 1:
         dist.destroy_process_group()
