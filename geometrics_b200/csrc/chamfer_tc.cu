@@ -57,11 +57,22 @@ constexpr float kBigNorm = 1.0e30f;  // padding candidates: approximate distance
 // Rows past `cnt` (padding up to a multiple of kRowsPerCta): A form zero.  Rows past `cnt_scan` (padding and
 // the reference's skipped tail): B form zero with n1 = kBigNorm, so they can never be a minimum.
 // Storage order (uint4 units): [batch item][128-row block][k-chunk][row in block].
-__global__ void __launch_bounds__(256)
-pack_kernel(int b, int cnt, int cnt_scan, int cnt_pad, const float *__restrict__ xyz, uint4 *__restrict__ formA,
-            uint4 *__restrict__ formB, unsigned *__restrict__ rmax_bits)
+struct PackSet {
+    const float *xyz;
+    uint4 *formA, *formB;
+    int cnt, cnt_scan, cnt_pad;
+    unsigned blocks;  // thread blocks of this set
+};
+// One launch packs both point sets (blockIdx.x < sets[0].blocks: the first).
+__global__ void __launch_bounds__(256) pack_kernel(int b, const PackSet s0, const PackSet s1, unsigned *__restrict__ rmax_bits)
 {
-    const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+    const bool second = blockIdx.x >= s0.blocks;
+    const PackSet &ps = second ? s1 : s0;
+    const int cnt = ps.cnt, cnt_scan = ps.cnt_scan, cnt_pad = ps.cnt_pad;
+    const float *__restrict__ xyz = ps.xyz;
+    uint4 *__restrict__ formA = ps.formA;
+    uint4 *__restrict__ formB = ps.formB;
+    const long long t = (long long)(blockIdx.x - (second ? s0.blocks : 0u)) * 256 + threadIdx.x;
     float amax = 0.f;
     if (t < (long long)b * cnt_pad) {
         const int bi = (int)(t / cnt_pad), r = (int)(t % cnt_pad);
@@ -70,6 +81,7 @@ pack_kernel(int b, int cnt, int cnt_scan, int cnt_pad, const float *__restrict__
             const float *p = xyz + ((size_t)bi * cnt + r) * 3;
             const float x = p[0], y = p[1], z = p[2];
             amax = fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z));
+            if (!(fabsf(x) + fabsf(y) + fabsf(z) < __int_as_float(0x7f800000))) amax = __int_as_float(0x7f800000);  // NaN too (fmaxf drops NaN)
             const float xh = bf16_val(x), yh = bf16_val(y), zh = bf16_val(z);
             const float xl = x - xh, yl = y - yh, zl = z - zh;  // exact; rounded to bf16 when packed
             const float nn = fmaf(z, z, fmaf(x, x, y * y));
@@ -449,8 +461,12 @@ cudaError_t launch(int b, int n, const float *xyz1, int m, const float *xyz2, in
     if (e != cudaSuccess) return e;
     {
         prof::Scope ps(st, prof::kChamferTcPack);
-        pack_kernel<<<(unsigned)(((size_t)b * np + 255) / 256), 256, 0, st>>>(b, n, n_scan, (int)np, xyz1, a1, b1, rmax);
-        pack_kernel<<<(unsigned)(((size_t)b * mp + 255) / 256), 256, 0, st>>>(b, m, m_scan, (int)mp, xyz2, a2, b2, rmax);
+        PackSet p0, p1;
+        p0.xyz = xyz1, p0.formA = a1, p0.formB = b1, p0.cnt = n, p0.cnt_scan = n_scan, p0.cnt_pad = (int)np;
+        p0.blocks = (unsigned)(((size_t)b * np + 255) / 256);
+        p1.xyz = xyz2, p1.formA = a2, p1.formB = b2, p1.cnt = m, p1.cnt_scan = m_scan, p1.cnt_pad = (int)mp;
+        p1.blocks = (unsigned)(((size_t)b * mp + 255) / 256);
+        pack_kernel<<<p0.blocks + p1.blocks, 256, 0, st>>>(b, p0, p1, rmax);
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     SearchArgs2 s;

@@ -32,7 +32,8 @@ __global__ void __launch_bounds__(kThreads)
 loss_partial_kernel(int b, int n, const float *__restrict__ xyz1, int m, const float *__restrict__ xyz2,
                     const int *__restrict__ idx1, const int *__restrict__ idx2,
                     float *__restrict__ d1_out, float *__restrict__ d2_out, double2 *__restrict__ partial,
-                    float f1_scale, float f1_thr, int *__restrict__ cnt1, int *__restrict__ cnt2)
+                    float f1_scale, float f1_thr, int *__restrict__ cnt1, int *__restrict__ cnt2,
+                    unsigned *__restrict__ arrive, float *__restrict__ sums)
 {
     const long long rows1 = (long long)b * n, rows2 = (long long)b * m;
     const int lane = threadIdx.x & 31;
@@ -93,31 +94,35 @@ loss_partial_kernel(int b, int n, const float *__restrict__ xyz1, int m, const f
         }
         partial[blockIdx.x] = make_double2(a, c);
     }
-}
-
-// Fixed-order final sum (deterministic): sums[0] = s1, sums[1] = s2.
-__global__ void __launch_bounds__(256) loss_final_kernel(const double2 *__restrict__ partial, int nblocks,
-                                                          float *__restrict__ sums)
-{
-    __shared__ double sa[256], sc[256];
+    // the last block to arrive adds the partials in a fixed order (deterministic) -- no second launch
+    __shared__ bool last;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last = atomicAdd(arrive, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    __shared__ double sa[kThreads], sc[kThreads];
     double a = 0, c = 0;
-    for (int i = threadIdx.x; i < nblocks; i += 256) {
-        a += partial[i].x;
-        c += partial[i].y;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += kThreads) {
+        a += __ldcg(&partial[i].x);  // L2 reads: the partials were written by other blocks
+        c += __ldcg(&partial[i].y);
     }
     sa[threadIdx.x] = a;
     sc[threadIdx.x] = c;
     __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
-        if (threadIdx.x < s) {
-            sa[threadIdx.x] += sa[threadIdx.x + s];
-            sc[threadIdx.x] += sc[threadIdx.x + s];
+    for (int st = kThreads / 2; st > 0; st >>= 1) {
+        if (threadIdx.x < st) {
+            sa[threadIdx.x] += sa[threadIdx.x + st];
+            sc[threadIdx.x] += sc[threadIdx.x + st];
         }
         __syncthreads();
     }
     if (threadIdx.x == 0) {
         sums[0] = (float)sa[0];
         sums[1] = (float)sc[0];
+        *arrive = 0u;  // ready for the next call on this workspace
     }
 }
 
@@ -169,7 +174,7 @@ using namespace geom;
 extern "C" size_t geom_chamfer_loss_workspace_bytes(int b, int n, int m)
 {
     if (b < 0 || n < 0 || m < 0) return 0;
-    return sizeof(double2) * (size_t)loss::blocks_for((long long)b * ((long long)n + m));
+    return sizeof(double2) * (size_t)loss::blocks_for((long long)b * ((long long)n + m)) + 16;  // partials + arrival counter
 }
 
 static int chamfer_loss_fwd_impl(int b, int n, const float *xyz1, int m, const float *xyz2, const int *idx1, const int *idx2,
@@ -191,13 +196,14 @@ static int chamfer_loss_fwd_impl(int b, int n, const float *xyz1, int m, const f
     if (items == 0 || n == 0 || m == 0) return status_from_cuda(cudaMemsetAsync(sums, 0, 2 * sizeof(float), st));
     if (!xyz1 || !xyz2 || !idx1 || !idx2) return GEOM_ERR_INVALID_ARG;
     const int blocks = blocks_for(items);
-    if (!workspace || workspace_bytes < sizeof(double2) * (size_t)blocks || ((uintptr_t)workspace & 15u))
+    if (!workspace || workspace_bytes < sizeof(double2) * (size_t)blocks + 16 || ((uintptr_t)workspace & 15u))
         return GEOM_ERR_WORKSPACE;
+    unsigned *arrive = (unsigned *)((double2 *)workspace + blocks);
+    if ((e = cudaMemsetAsync(arrive, 0, 4, st)) != cudaSuccess) return status_from_cuda(e);
     {
         prof::Scope ps(st, prof::kChamferLoss);
         loss_partial_kernel<<<blocks, kThreads, 0, st>>>(b, n, xyz1, m, xyz2, idx1, idx2, dist1, dist2, (double2 *)workspace,
-                                                         f1_scale, f1_thr, count1, count2);
-        loss_final_kernel<<<1, 256, 0, st>>>((const double2 *)workspace, blocks, sums);
+                                                         f1_scale, f1_thr, count1, count2, arrive, sums);
     }
     return status_from_cuda(cudaGetLastError());
 }

@@ -320,3 +320,19 @@ def test_nonfinite_inputs_match_reference_cuda(ref_cuda, cuda):
         for a_, b_ in zip(got, want):
             assert_same_f32(a_.cpu().numpy().view(np.float32) if a_.dtype == torch.float32 else a_.cpu().numpy().astype(np.float32),
                             b_.cpu().numpy().view(np.float32) if b_.dtype == torch.float32 else b_.cpu().numpy().astype(np.float32), str(kw))
+
+
+@pytest.mark.parametrize("mode", [dict(), dict(tensor=False)], ids=["tensor", "cuda_cores"])
+def test_nan_only_input_is_detected(oracle, cuda, mode):
+    """A single NaN coordinate (no Inf anywhere) must trigger the non-finite slow path too: fmaxf-style range scans drop
+    NaNs, so the detection has to propagate them explicitly."""
+    x1, x2 = chamfer_inputs("random", 1, 700, 1100, 93)
+    x2[0, 512, 1] = float("nan")   # first candidate of the second 512-tile
+    x1[0, 0, 2] = float("nan")
+    got = _run(x1, x2, cuda, **mode)
+    want = oracle.chamfer_fwd(x1.numpy(), x2.numpy())
+    for name, g_, w_ in zip(("dist1", "idx1", "dist2", "idx2"), got, want):
+        if name.startswith("dist"):
+            assert_same_f32(g_, w_, name)
+        else:
+            assert (g_ == w_).all(), f"{name}: {np.count_nonzero(g_ != w_)} of {w_.size} indices differ"
