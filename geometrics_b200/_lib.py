@@ -50,6 +50,7 @@ SYMBOLS = {
     "geom_chamfer_loss_f1_fwd": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, C.c_float, C.c_float, _vp, _vp, _vp, _sz, _vp]),
     "geom_chamfer_loss_bwd": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "geom_debug_set": (_i, [_i, C.c_float]),
+    "geom_debug_tc_dump": (_i, [_i, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "geom_tri_workspace_bytes": (_sz, [_i, _i]),
     "geom_tri_tensor_workspace_bytes": (_sz, [_i, _i, _i]),
     "geom_tri_fwd": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _u, _vp]),

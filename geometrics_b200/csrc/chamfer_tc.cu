@@ -405,6 +405,64 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 bot
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((unsigned)kTmemCols));
 }
 
+// Test hook (geom_debug_tc_dump): the approximate squared distances exactly as the tensor core delivers them -- one CTA,
+// one 128-row query block against every 64-candidate half tile, accumulators read back from TMEM and stored.  Lets a test
+// assert the filter's error bound |dt - d| <= eps on the hardware itself instead of on a numpy model of it.
+__global__ void __launch_bounds__(128) dump_kernel(const uint4 *__restrict__ formA, const uint4 *__restrict__ formB, int nc_pad,
+                                                   float *__restrict__ out)
+{
+    __shared__ __align__(128) uint4 sA[2][128];
+    __shared__ __align__(128) uint4 sB[2][kHalfCols];
+    __shared__ __align__(8) unsigned long long bar;
+    __shared__ unsigned tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(64u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    sA[0][tid] = formA[tid];
+    sA[1][tid] = formA[128 + tid];
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem = tmem_slot;
+    const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(kHalfCols >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
+    unsigned phase = 0;
+    for (int c0 = 0; c0 < nc_pad; c0 += kHalfCols) {
+        // half tile c0..c0+63 of the packed candidates: block (c0 / 128), rows (c0 % 128)..+63 of both k-chunks
+        const uint4 *blk = formB + (size_t)(c0 / 128) * 256 + (c0 % 128);
+        if (tid < kHalfCols) {
+            sB[0][tid] = blk[tid];
+            sB[1][tid] = blk[128 + tid];
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (tid == 0) {
+            const u64 da = make_desc(smem_u32(&sA[0][0]), 128 * 16, 128);
+            const u64 db = make_desc(smem_u32(&sB[0][0]), kHalfCols * 16, 128);
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem),
+                         "l"(da), "l"(db), "r"(idesc), "r"(0u)
+                         : "memory");
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+        }
+        mbar_wait(&bar, phase);
+        phase ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        unsigned v[64];
+        tmem_ld64_wait(v, tmem + ((unsigned)(warp * 32) << 16));
+        for (int k = 0; k < 64; ++k) out[(size_t)(warp * 32 + lane) * nc_pad + c0 + k] = __uint_as_float(v[k]);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+    }
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64u));
+}
+
 static size_t pad_rows(int cnt) { return ((size_t)cnt + kRowsPerCta - 1) / kRowsPerCta * kRowsPerCta; }
 
 size_t workspace_bytes(int b, int n, int m)
@@ -519,5 +577,39 @@ cudaError_t launch(int b, int n, const float *xyz1, int m, const float *xyz2, in
     return cudaGetLastError();
 }
 
+// dt (128 x pad128(m)) = approximate squared distances of the first min(n, 128) points of xyz1 (one batch item) against the
+// m points of xyz2, as the MMA computes them; *rmax = R.  workspace >= workspace_bytes(1, 128, m).
+cudaError_t debug_dump(int n, const float *xyz1, int m, const float *xyz2, float *dt, float *rmax_out, void *workspace,
+                       cudaStream_t st)
+{
+    const size_t np = pad_rows(n < 128 ? n : 128), mp = pad_rows(m);
+    char *w = (char *)workspace;
+    unsigned *rmax = (unsigned *)w;
+    uint4 *a1 = (uint4 *)(w + 256);
+    uint4 *b1 = a1 + np * 2;
+    uint4 *a2 = b1 + np * 2;
+    uint4 *b2 = a2 + mp * 2;
+    cudaError_t e = cudaMemsetAsync(rmax, 0, 256, st);
+    if (e != cudaSuccess) return e;
+    PackSet p0, p1;
+    p0.xyz = xyz1, p0.formA = a1, p0.formB = b1, p0.cnt = n < 128 ? n : 128, p0.cnt_scan = p0.cnt, p0.cnt_pad = (int)np;
+    p0.blocks = (unsigned)((np + 255) / 256);
+    p1.xyz = xyz2, p1.formA = a2, p1.formB = b2, p1.cnt = m, p1.cnt_scan = m, p1.cnt_pad = (int)mp;
+    p1.blocks = (unsigned)((mp + 255) / 256);
+    pack_kernel<<<p0.blocks + p1.blocks, 256, 0, st>>>(1, p0, p1, rmax);
+    const int nc_pad = (int)((m + 127) / 128 * 128);
+    dump_kernel<<<1, 128, 0, st>>>(a1, b2, nc_pad, dt);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    return cudaMemcpyAsync(rmax_out, rmax, 4, cudaMemcpyDeviceToDevice, st);
+}
+
 }  // namespace chamfer_tc
 }  // namespace geom
+
+extern "C" int geom_debug_tc_dump(int n, const float *xyz1, int m, const float *xyz2, float *dt, float *rmax, void *workspace,
+                                  size_t workspace_bytes, geom_stream_t stream)
+{
+    if (n <= 0 || m <= 0 || !xyz1 || !xyz2 || !dt || !rmax) return GEOM_ERR_INVALID_ARG;
+    if (!workspace || workspace_bytes < geom::chamfer_tc::workspace_bytes(1, 128, m) || ((uintptr_t)workspace & 15u)) return GEOM_ERR_WORKSPACE;
+    return geom::status_from_cuda(geom::chamfer_tc::debug_dump(n, xyz1, m, xyz2, dt, rmax, workspace, (cudaStream_t)stream));
+}

@@ -89,6 +89,12 @@ GEOM_API const char *geom_prof_kernel_name(int id);
 #define GEOM_DEBUG_TC_CHUNKS 7          /* Chamfer tensor-core search: CTAs per row block (1..8; candidate split) */
 #define GEOM_DEBUG_KNOBS 8
 GEOM_API int geom_debug_set(int knob, float value);
+/* Test hook: dt (128, pad128(m)) row-major = the approximate squared distances of the first min(n,128) points of xyz1
+ * (n,3) against xyz2 (m,3) exactly as the tensor-core filter computes them (bf16 split operands, tcgen05.mma, fp32
+ * accumulation in TMEM), *rmax = R (largest |coordinate|), both in DEVICE memory.  tests/test_gpu_chamfer.py asserts the
+ * filter's error bound |dt - d| <= 2.5e-4 R^2 / 3 on it.  workspace >= geom_chamfer_tensor_workspace_bytes(1, 128, m). */
+GEOM_API int geom_debug_tc_dump(int n, const float *xyz1, int m, const float *xyz2, float *dt, float *rmax,
+                       void *workspace, size_t workspace_bytes, geom_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Chamfer nearest-neighbour search.
