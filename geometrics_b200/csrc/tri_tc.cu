@@ -26,7 +26,7 @@
 //      the triangle with the smallest fp32 sphere distance in that tile and evaluates it exactly: U, a tight
 //      upper bound on the point's final distance, available before anything is listed.
 //      Pass 2 lists (tile, 16-bit mask of its 8-triangle groups) for the groups whose minimum h satisfies
-//          h <= s^2 + 2 s r_max + eps,   s = sqrt(U) (1 + 1e-3) + 1e-4 R,   r_max = largest radius of the mesh
+//          h <= s^2 + 2 s r_max + eps,   s = sqrt(U) (1 + 1e-3) + 1e-4 R,   r_max = largest radius in the tile
 //      (h > that  =>  |p - c_j| - r_j > s  =>  d_j > U, so the triangle cannot win or tie).  Listed groups are
 //      re-tested per triangle with the fp32 sphere (its own r_j, no eps) and the survivors are evaluated with the
 //      reference arithmetic; U tightens as better triangles are found.  Selection rule: smaller distance wins,
@@ -194,13 +194,14 @@ __global__ void __launch_bounds__(256) prep_kernel(const PrepArgs a)
         a.nrm[t] = nv;
         float4 *rp = a.rec + (size_t)t * kRecVec4;
         rp[0] = r0, rp[1] = r1, rp[2] = r2, rp[3] = r3;
-        // m_pad is a multiple of 128, so a warp never straddles two meshes: one atomic per warp for the largest radius
+        // m_pad is a multiple of 128, so a warp never straddles two meshes (nor two tiles)
         rwarp = fmaxf(rwarp, __shfl_xor_sync(0xffffffffu, rwarp, 16));
         rwarp = fmaxf(rwarp, __shfl_xor_sync(0xffffffffu, rwarp, 8));
         rwarp = fmaxf(rwarp, __shfl_xor_sync(0xffffffffu, rwarp, 4));
         rwarp = fmaxf(rwarp, __shfl_xor_sync(0xffffffffu, rwarp, 2));
         rwarp = fmaxf(rwarp, __shfl_xor_sync(0xffffffffu, rwarp, 1));
-        if ((threadIdx.x & 31) == 0 && rwarp > 0.f) atomicMax(a.ritem_bits + bi, __float_as_uint(rwarp));  // >= 0: bits order like values
+        // one atomic per warp for the largest radius of the 128-triangle TILE (a warp's 32 triangles share it)
+        if ((threadIdx.x & 31) == 0 && rwarp > 0.f) atomicMax(a.ritem_bits + (size_t)bi * a.ntiles128 + (j >> 7), __float_as_uint(rwarp));
     }
     amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 16));
     amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 8));
@@ -406,7 +407,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const ScanArgs a)
             p = v3(q[0], q[1], q[2]);
         }
         const float R = __uint_as_float(*a.rmax_bits);
-        const float rmesh = __uint_as_float(a.ritem_bits[bi]);
+        const unsigned *rtile = a.ritem_bits + (size_t)bi * a.ntiles128;  // largest sphere radius per 128-triangle tile
         const float pmax = fabsf(p.x) + fabsf(p.y) + fabsf(p.z);  // NaN / inf propagate
         // the filter needs finite operands of a magnitude the bf16 split handles; anything else: the reference loop below
         const bool filter_ok = (R < 1.0e15f) && (R > 1.0e-15f) && (pmax < kInf);  // false on NaN
@@ -425,7 +426,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const ScanArgs a)
 #ifdef TRI_TC_TIMING
         unsigned long long tt_[16] = {};
 #endif
-        float thr = active ? kInf : -kInf;  // listing threshold on h; -inf: this thread lists nothing
+        float thr0 = active ? kInf : -kInf, thr1 = 0.f;  // listing threshold on h (see below); -inf: this thread lists nothing
         bool poisoned = false;   // the first triangle of reference tile 0 evaluates to NaN for this point (:194,:202)
         bool dead_now = false;   // the same for the reference tile being swept: nothing in it can be selected
 
@@ -517,7 +518,9 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const ScanArgs a)
             const float u0 = (k0 == ~0ull) ? kInf : __uint_as_float((unsigned)(k0 >> 32));
             const float sUp = fmaf(sqrtf(u0), 1.0f + kRelMargin, kAbsMargin * R);
             S.b2[tid] = sUp * sUp;
-            thr = active ? fmaf(sUp, sUp, fmaf(2.0f * sUp, rmesh, eps)) : -kInf;
+            // per tile t: thr = s^2 + 2 s r_tile(t) + eps = thr0 + thr1 * r_tile(t)
+            thr0 = active ? fmaf(sUp, sUp, eps) : -kInf;
+            thr1 = active ? 2.0f * sUp : 0.0f;
         }
         __syncwarp();
         TT_STAMP(2);
@@ -544,6 +547,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const ScanArgs a)
             const int tt = ntiles + t;
             const unsigned ti = __ldg(tinfo + t);
             check_first(t, ti);
+            const float thr = fmaf(thr1, __uint_as_float(__ldg(rtile + t)), thr0);  // inf stays inf, -inf stays -inf (thr1 = 0)
             unsigned mask = 0;
             {
                 unsigned v[64];
@@ -726,7 +730,7 @@ static Layout layout(int b, int n, int m)
     L.m_pad = pad_to((size_t)m, kTileCols);
     size_t o = 256;  // [0]: R bits
     L.off_ritem = o;
-    o += pad_to((size_t)b * 4, 256);
+    o += pad_to((size_t)b * (L.m_pad / kTileCols) * 4, 256);  // largest radius per tile
     L.off_tinfo = o;
     o += pad_to((size_t)b * (L.m_pad / kTileCols) * 4, 256);
     L.off_formA = o;

@@ -180,7 +180,9 @@ class BnReluResFunction(torch.autograd.Function):
         dev = xc.device
         ld_res = 0
         if res is not None:
-            if res.shape != xc.shape or res.stride(2) != 1 or res.stride(0) != v * res.stride(1):
+            if res.shape != xc.shape:
+                raise ValueError(f"residual {tuple(res.shape)} does not match x {tuple(xc.shape)}")
+            if res.stride(2) != 1 or res.stride(0) != v * res.stride(1):
                 res = res.contiguous()
             ld_res = res.stride(1)
         with _lib.on_device(dev):
@@ -246,7 +248,9 @@ class GcnBnStageFunction(torch.autograd.Function):
         dev = xc.device
         ld_res = 0
         if res is not None:
-            if res.shape != (b, v, fout) or res.stride(2) != 1 or res.stride(0) != v * res.stride(1):
+            if tuple(res.shape) != (b, v, fout):
+                raise ValueError(f"residual {tuple(res.shape)} does not match the stage output {(b, v, fout)}")
+            if res.stride(2) != 1 or res.stride(0) != v * res.stride(1):
                 res = res.contiguous()
             ld_res = res.stride(1)
         ptr = lambda t: t.data_ptr() if t is not None else None  # noqa: E731

@@ -166,7 +166,7 @@ def test_block_backward_runs_and_matches_torch_stack(cuda, setup, tensor, monkey
     import geometrics_b200 as g
 
     monkeypatch.setattr(g.layers, "TENSOR_GEMM", tensor)
-    ptol, wtol = (5e-3, 1e-2) if tensor else (1e-3, 2e-3)
+    ptol, wtol = (5e-3, 2e-2) if tensor else (1e-3, 2e-3)  # tensor arm: a ReLU mask flip next to zero moves a whole gradient entry
 
     mods, adj, pos, pooled, _ = setup
     block = mods["block"]
@@ -182,6 +182,9 @@ def test_block_backward_runs_and_matches_torch_stack(cuda, setup, tensor, monkey
     block.zero_grad()
     orig = g.layers.zeron_gcn
     try:
+        # reference arm: the dense-adjacency torch expression for every layer AND torch's own BatchNorm1d / relu / add / div
+        # (FUSED_BN off: otherwise the fused stage node would bypass layers.zeron_gcn and the comparison would be vacuous)
+        block.FUSED_BN = False
         g.layers.zeron_gcn = lambda x, w, b, a, split, act=None: (lambda y: y if act is None else act(y))(
             R.zeron_gcn(x, w[0] if w.dim() == 3 else w, b, dense_adj, split))
         p2 = pos.clone().requires_grad_(True)
@@ -189,6 +192,7 @@ def test_block_backward_runs_and_matches_torch_stack(cuda, setup, tensor, monkey
         (c2.sum() + f2.mean()).backward()
     finally:
         g.layers.zeron_gcn = orig
+        del block.FUSED_BN
     close(c1, c2.detach().cpu().numpy(), 2e-4, "coords")
     close(gp1, p2.grad.cpu().numpy(), ptol, "d positions")
     g_dense = [p.grad for p in block.parameters() if p.grad is not None]
@@ -355,3 +359,54 @@ def test_gcn_backward_kernels_vs_torch(cuda, shape):
         grads.append((x.grad, w.grad, bias.grad))
     for name, a, r in zip(("dX", "dW", "db"), grads[1], grads[0]):
         assert float((a - r).abs().max()) <= 2e-5 * max(1e-3, float(r.abs().max())), (name, float((a - r).abs().max()), float(r.abs().max()))
+
+
+@pytest.mark.parametrize("tensor", [False, True], ids=["cuda-core", "tensor-core"])
+@pytest.mark.parametrize("stage_node", [True, False], ids=["one-node-per-stage", "two-nodes"])
+def test_block_train_mode_batch4_vs_torch_stack(cuda, tensor, stage_node, monkeypatch):
+    """TRAIN-mode BatchNorm at a batch of 4 (a batch of 2 makes BatchNorm1d(V) a sign function; verdict item): the whole
+    block -- 14 layers, 13 fused BN/ReLU/residual stages -- against the reference composition (dense-adjacency torch layers,
+    nn.BatchNorm1d, F.relu, (a + b) / 2) with shared weights: outputs, every gradient, and the BatchNorm running statistics
+    after the step.  Error budget: ~1e-6 relative per 3xTF32 GEMM and per fused stage, 27 of them chained through
+    normalisations of O(1) gain: 2e-4 on outputs (the golden tests' bound), 2e-3 on gradients."""
+    import copy
+
+    import geometrics_b200 as g
+    from geometrics_b200 import synth
+
+    monkeypatch.setattr(g.layers, "TENSOR_GEMM", tensor)
+    v, f = synth.icosphere(2)
+    adj = g.adj_init(f)["adj"].to(cuda)
+    V = v.shape[0]
+    torch.manual_seed(3)
+    block = g.BatchMeshDeformationBlock(3 + 125, V, hidden=96).to(cuda).train()  # models.py:246 needs in_features >= hidden
+    ref_block = copy.deepcopy(block)
+    ref_block.FUSED_BN = False
+    block.FUSED_STAGE = stage_node
+    pos0 = synth.mesh_batch(v, 4).to(cuda)
+    pooled0 = 0.3 * torch.randn(4, V, 125, device=cuda)
+    outs = []
+    orig = g.layers.zeron_gcn
+    for blk, dense in ((block, False), (ref_block, True)):
+        pos, pooled = pos0.clone().requires_grad_(True), pooled0.clone().requires_grad_(True)
+        try:
+            if dense:
+                g.layers.zeron_gcn = lambda x, w, b, a, split, act=None: (lambda y: y if act is None else act(y))(
+                    R.zeron_gcn(x, w[0] if w.dim() == 3 else w, b, adj, split))
+            feats, coords = blk(pos, pooled, adj)
+            (coords.sum() + (feats ** 2).mean()).backward()
+        finally:
+            g.layers.zeron_gcn = orig
+        outs.append(dict(coords=coords.detach(), feats=feats.detach(), dpos=pos.grad, dpooled=pooled.grad,
+                         params={n: p.grad for n, p in blk.named_parameters() if p.grad is not None},
+                         stats={n: b_.clone() for n, b_ in blk.named_buffers()}))
+    a, r = outs
+    for key, tol in (("coords", 2e-4), ("feats", 2e-4), ("dpos", 2e-3), ("dpooled", 2e-3)):
+        close(a[key], r[key].cpu().numpy(), tol, key)
+    assert a["params"].keys() == r["params"].keys()
+    for n in r["params"]:
+        close(a["params"][n], r["params"][n].cpu().numpy(), 2e-3, n)
+    for n in r["stats"]:
+        if n.startswith("bn14"):
+            continue  # never used in forward (models.py:235)
+        close(a["stats"][n].float(), r["stats"][n].float().cpu().numpy(), 1e-4, n)
