@@ -41,8 +41,8 @@ constexpr int kGroups = 4;                      // 128-row blocks per CTA == sca
 constexpr int kRowsPerCta = 128 * kGroups;
 constexpr int kTileCols = 128;                  // candidates per ring stage (one packed block)
 constexpr int kHalfCols = 64;                   // candidates per MMA / accumulator
-constexpr int kScanThreads = kGroups * 128;     // warps 0-15: scanners
-constexpr int kThreads = kScanThreads + kGroups * 32;  // warps 16-19: one producer per group
+constexpr int kScanThreads = kGroups * 128;     // scanner warps come first
+constexpr int kThreads = kScanThreads + kGroups * 32;  // + one producer warp per row block
 constexpr int kStages = 8;                      // candidate-tile ring (TMA)
 constexpr int kPrefetch = kStages - 2;          // tiles in flight ahead of the MMAs
 constexpr int kEvCap = 16;                      // events (listed tiles) per thread held in shared memory
@@ -110,6 +110,17 @@ __global__ void __launch_bounds__(256) pack_kernel(int b, const PackSet s0, cons
     amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
     if ((threadIdx.x & 31) == 0 && amax > 0.f) atomicMax(rmax_bits, __float_as_uint(amax));  // amax >= 0: bits order like values
 }
+
+#ifdef CH_TIMING
+__device__ unsigned long long g_ch_timing[256 * 20 * 8];
+#define CT_DECL unsigned long long ct_[8] = {}; unsigned long long ct_t_ = clock64()
+#define CT_LAP(slot) do { const unsigned long long n_ = clock64(); ct_[slot] += n_ - ct_t_; ct_t_ = n_; } while (0)
+#define CT_DUMP do { if (lane == 0 && blockIdx.x < 256) for (int i_ = 0; i_ < 8; ++i_) g_ch_timing[((size_t)blockIdx.x * 20 + warp) * 8 + i_] = ct_[i_]; } while (0)
+#else
+#define CT_DECL do { } while (0)
+#define CT_LAP(slot) do { } while (0)
+#define CT_DUMP do { } while (0)
+#endif
 
 struct SearchArgs {
     const float *qxyz;    // exact query points   (b, nq, 3)
@@ -198,7 +209,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 bot
         mbar_init(&S.a_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // barrier words visible to the TMA unit
-        // the CTA's four packed query blocks are contiguous: one 16 KB copy; then the head of the candidate ring
+        // the CTA's packed query blocks are contiguous: one copy; then the head of the candidate ring
         tma_load(&S.sA[0][0][0], a.formA + ((size_t)bi * a.nq_pad + row0) * 2, kGroups * kBlockBytes, &S.a_full);
         for (int t = 0; t < kPrefetch && t < ntiles; ++t)
             tma_load(&S.sB[t][0][0], gB + (size_t)t * 256, kBlockBytes, &S.b_full[t]);
@@ -210,39 +221,48 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 bot
 
     if (warp >= kGroups * 4) {
         // ================================ producers (one warp per row block) ================================
-        const int g = warp - kGroups * 4;
+        // warp-uniform by construction (and visibly so to ptxas): the MMA operands then live in uniform registers and the
+        // issue is one predicated instruction instead of a per-lane R2UR loop
+        const int g = __shfl_sync(0xffffffffu, warp, 0) - kGroups * 4;
+        const unsigned tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
         // D = f32, A = B = bf16, both K-major, N = 64, M = 128
         const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(kHalfCols >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
         const u64 da = make_desc(smem_u32(&S.sA[g][0][0]), 128 * 16, 128);
         mbar_wait(&S.a_full, 0);
+        CT_DECL;
         for (int t = 0; t < ntiles; ++t) {
             const int s = t % kStages;
-            if (g == 0) {
-                // ring refill: tile t+kPrefetch goes to the stage of tile t-2, once every group is done with it
+            if ((t & (kGroups - 1)) == g) {
+                // ring refill, taken in turns by the producers (one doing all of it would be the slowest chain of the CTA):
+                // tile t+kPrefetch goes to the stage of tile t-2, once every group is done with it
                 const int tl = t + kPrefetch;
                 if (tl < ntiles) {
-                    if (t >= 2) mbar_wait(&S.b_free[tl % kStages], (unsigned)(((t - 2) / kStages) & 1));
-                    if (lane == 0) tma_load(&S.sB[tl % kStages][0][0], gB + (size_t)tl * 256, kBlockBytes, &S.b_full[tl % kStages]);
+                    if (t >= 2) mbar_wait_fast(&S.b_free[tl % kStages], (unsigned)(((t - 2) / kStages) & 1));
+                    tma_load_elect(&S.sB[tl % kStages][0][0], gB + (size_t)tl * 256, kBlockBytes, &S.b_full[tl % kStages]);
                 }
             }
+            CT_LAP(0);
             mbar_wait(&S.b_full[s], (unsigned)((t / kStages) & 1));
+            CT_LAP(1);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 // accumulator (g, h) was last read by the scanners of tile t-1
                 if (t >= 1) mbar_wait(&S.empty_bar[g][h], (unsigned)((t - 1) & 1));
+                CT_LAP(2 + 2 * h);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (lane == 0) {
+                {
                     const u64 db = make_desc(smem_u32(&S.sB[s][0][h * kHalfCols]), kTileCols * 16, 128);
                     asm volatile(
-                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem + (unsigned)((g * 2 + h) * kHalfCols)),
-                        "l"(da), "l"(db), "r"(idesc), "r"(0u)
+                        "{\n\t.reg .pred p, pe;\n\telect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+                        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n\t}" ::"r"(tmem_u + (unsigned)((g * 2 + h) * kHalfCols)),
+                        "l"(da), "l"(db), "r"(idesc), "r"(0u), "r"(smem_u32(&S.full_bar[g][h]))
                         : "memory");
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&S.full_bar[g][h])) : "memory");
                 }
-                __syncwarp();
+                CT_LAP(3 + 2 * h);
             }
         }
+        CT_DUMP;
     } else {
         // ================================ scanners ================================
         const int g = warp >> 2;                  // row block == warp group
@@ -323,13 +343,17 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 bot
         const unsigned tbase = tmem + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(g * 2 * kHalfCols);
         const unsigned bfree0 = smem_u32(&S.b_free[0]);
         const bool group_leader = (warp & 3) == 0 && lane == 0;
+        CT_DECL;
         for (int t = 0; t < ntiles; ++t) {
             float bm0, bm1, bm2, bm3;
             {
+                CT_LAP(5);
                 mbar_wait(&S.full_bar[g][0], (unsigned)(t & 1));
+                CT_LAP(0);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 unsigned v[64];
                 tmem_ld64_wait(v, tbase);
+                CT_LAP(1);
                 // the values are in registers: hand the accumulator back to the tensor core
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
@@ -338,12 +362,15 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 bot
                 bm1 = tree_min32(v, 32);
             }
             {
+                CT_LAP(2);
                 mbar_wait(&S.full_bar[g][1], (unsigned)(t & 1));
+                CT_LAP(3);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 // both MMAs of this group on tile t are complete: the group no longer reads the ring stage
                 if (group_leader) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bfree0 + 8u * (unsigned)(t % kStages)) : "memory");
                 unsigned v[64];
                 tmem_ld64_wait(v, tbase + (unsigned)kHalfCols);
+                CT_LAP(4);
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&S.empty_bar[g][1]);
@@ -360,7 +387,10 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 bot
             }
             if (cnt >= kEvCap) flush();
         }
+        CT_LAP(5);
         flush();
+        CT_LAP(6);
+        CT_DUMP;
         const size_t off = (size_t)bi * a.nq + qrow;
         bool write = valid;
         int dirsel_, bi_, rblock, chunk, nchunks;  // recomputed: nothing of the grid decode stays live through the sweep
@@ -462,6 +492,17 @@ __global__ void __launch_bounds__(128) dump_kernel(const uint4 *__restrict__ for
     }
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64u));
 }
+
+}  // namespace chamfer_tc
+}  // namespace geom
+#ifdef CH_TIMING
+extern "C" __attribute__((visibility("default"))) int geom_debug_read_ch_timing(unsigned long long *host, size_t count)
+{
+    return (int)cudaMemcpyFromSymbol(host, geom::chamfer_tc::g_ch_timing, count * sizeof(unsigned long long));
+}
+#endif
+namespace geom {
+namespace chamfer_tc {
 
 static size_t pad_rows(int cnt) { return ((size_t)cnt + kRowsPerCta - 1) / kRowsPerCta * kRowsPerCta; }
 

@@ -37,6 +37,7 @@ __device__ __forceinline__ void tmem_ld64_wait(unsigned (&v)[64], unsigned taddr
                  : "memory");
 }
 
+
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -74,6 +75,17 @@ __device__ __forceinline__ void tma_load(void *smem_dst, const void *gmem_src, u
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
                  "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+// The same, called by a whole (converged) warp: one elected lane announces and issues the copy.  With warp-uniform
+// operands this compiles to straight-line code (UBLKCP on uniform registers) instead of a per-lane R2UR loop.
+__device__ __forceinline__ void tma_load_elect(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
+        "@pe mbarrier.arrive.expect_tx.shared::cta.b64 _, [%3], %2;\n\t"
+        "@pe cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}" ::"r"(smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
 }
 // the same in two steps, for several copies that complete one barrier phase: announce the bytes once, then copy
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)

@@ -365,7 +365,10 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const ScanArgs a)
 
     if (warp >= kGroups * 4) {
         // ================================ producers (one warp per point block) ================================
-        const int g = warp - kGroups * 4;
+        // warp-uniform, visibly to ptxas: the MMA operands live in uniform registers and the issue is one elected
+        // instruction instead of a per-lane R2UR loop
+        const int g = __shfl_sync(0xffffffffu, warp, 0) - kGroups * 4;
+        const unsigned tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
         const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(kHalfCols >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
         const u64 da = make_desc(smem_u32(&S.sA[g][0][0]), 128 * 16, 128);
         mbar_wait(&S.a_full, 0);
@@ -383,16 +386,15 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const ScanArgs a)
             for (int h = 0; h < 2; ++h) {
                 if (t >= 1) mbar_wait(&S.empty_bar[g][h], (unsigned)((t - 1) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (lane == 0) {
+                {
                     const u64 db = make_desc(smem_u32(&S.st[s].b[0][h * kHalfCols]), kTileCols * 16, 128);
                     asm volatile(
-                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem + (unsigned)((g * 2 + h) * kHalfCols)),
-                        "l"(da), "l"(db), "r"(idesc), "r"(0u)
+                        "{\n\t.reg .pred p, pe;\n\telect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+                        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n\t}" ::"r"(tmem_u + (unsigned)((g * 2 + h) * kHalfCols)),
+                        "l"(da), "l"(db), "r"(idesc), "r"(0u), "r"(smem_u32(&S.full_bar[g][h]))
                         : "memory");
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&S.full_bar[g][h])) : "memory");
                 }
-                __syncwarp();
             }
         }
     } else {
