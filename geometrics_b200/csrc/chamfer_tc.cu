@@ -291,50 +291,133 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 bot
         uint4 *evm = &S.evm[0][tid];
         unsigned *evt = &S.evt[0][tid];
 
-        // Exact re-evaluation of the listed tiles' 32-candidate blocks that are still inside the window.
-        // Pass 1 compacts the thread's surviving blocks to the front of its list (in place: at most four
-        // block ids per event, written behind the read position), so that pass 2 runs
-        // max-over-lanes(survivors) block evaluations per warp.
-        auto flush = [&]() {
+        CT_DECL;
+        // ---- exact re-evaluation of the listed tiles' 32-candidate blocks that are still inside the window ----
+        unsigned *blk = &S.evm[0][0].x;  // surviving block ids: evm[e][tid] reused as 4 x u32
+        auto blk_at = [&](int e) -> unsigned & { return blk[((size_t)(e >> 2) * kScanThreads + tid) * 4 + (e & 3)]; };
+        // Step 1: the thread's blocks with bm <= mt + 2 eps, compacted to the front of its list (in place: at most four block
+        // ids per event, written behind the read position).
+        auto list_blocks = [&]() -> int {
             const float thr = mt + eps2;
-            unsigned *blk = &S.evm[0][0].x;  // survivors: reuse evm[e][tid] as 4 x u32
             int keep = 0;
             for (int e = 0; e < cnt; ++e) {
                 const uint4 mb = evm[(size_t)e * kScanThreads];
                 const unsigned t4 = evt[(size_t)e * kScanThreads] * 4u;
-                // block ids of event e are written into evm[keep >> 2]: keep <= 4 e before the event, and
-                // event e has already been read, so slot (keep >> 2) <= e is free to overwrite
+                // block ids of event e go to evm[keep >> 2]: keep <= 4 e before the event, and event e has already been
+                // read, so slot (keep >> 2) <= e is free to overwrite
                 const float bms[4] = {__uint_as_float(mb.x), __uint_as_float(mb.y), __uint_as_float(mb.z), __uint_as_float(mb.w)};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     if (!(bms[i] > thr)) {  // NaN counts as inside
-                        blk[((size_t)(keep >> 2) * kScanThreads + tid) * 4 + (keep & 3)] = t4 + i;
+                        blk_at(keep) = t4 + i;
                         ++keep;
                     }
                 }
             }
-            for (int e = 0; e < keep; ++e) {
-                const int j0 = (int)blk[((size_t)(e >> 2) * kScanThreads + tid) * 4 + (e & 3)] * 32;
-                auto cand = [&](int j, float cx, float cy, float cz) {
-                    const float d = sqdist_ref(qx, qy, qz, cx, cy, cz);
-                    if (j < nc_loc && d < best) {  // ascending j + strict '<': lowest index among exact ties
-                        best = d;
-                        bidx = j;
-                    }
-                };
-                if (vec_ok && j0 + 32 <= nc_full_loc) {
-                    const float4 *p = reinterpret_cast<const float4 *>(cb + (size_t)j0 * 3);
+            return keep;
+        };
+        // Step 2 for one block: the reference's arithmetic on its 32 candidates, ascending index + strict '<' (lowest index
+        // among exact ties), for the query (x, y, z).
+        auto eval_block = [&](int j0, float x, float y, float z, float &bd, int &bj) {
+            auto cand = [&](int j, float cx, float cy, float cz) {
+                const float d = sqdist_ref(x, y, z, cx, cy, cz);
+                if (j < nc_loc && d < bd) {
+                    bd = d;
+                    bj = j;
+                }
+            };
+            if (vec_ok && j0 + 32 <= nc_full_loc) {
+                const float4 *p = reinterpret_cast<const float4 *>(cb + (size_t)j0 * 3);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float4 u0 = __ldg(p + 3 * i), u1 = __ldg(p + 3 * i + 1), u2 = __ldg(p + 3 * i + 2);
-                        cand(j0 + 4 * i, u0.x, u0.y, u0.z);
-                        cand(j0 + 4 * i + 1, u0.w, u1.x, u1.y);
-                        cand(j0 + 4 * i + 2, u1.z, u1.w, u2.x);
-                        cand(j0 + 4 * i + 3, u2.y, u2.z, u2.w);
+                for (int i = 0; i < 8; ++i) {
+                    const float4 u0 = __ldg(p + 3 * i), u1 = __ldg(p + 3 * i + 1), u2 = __ldg(p + 3 * i + 2);
+                    cand(j0 + 4 * i, u0.x, u0.y, u0.z);
+                    cand(j0 + 4 * i + 1, u0.w, u1.x, u1.y);
+                    cand(j0 + 4 * i + 2, u1.z, u1.w, u2.x);
+                    cand(j0 + 4 * i + 3, u2.y, u2.z, u2.w);
+                }
+            } else {
+                const int jend = min(j0 + 32, nc_loc);
+                for (int j = j0; j < jend; ++j) cand(j, __ldg(cb + (size_t)j * 3), __ldg(cb + (size_t)j * 3 + 1), __ldg(cb + (size_t)j * 3 + 2));
+            }
+        };
+        // Every thread evaluates its own blocks: max-over-lanes(blocks) rounds per warp.  Only the fallback.
+        auto flush_own = [&]() {
+            const int keep = list_blocks();
+            for (int e = 0; e < keep; ++e) eval_block((int)blk_at(e) * 32, qx, qy, qz, best, bidx);
+            cnt = 0;
+        };
+        // Inside the sweep a full list is only COMPACTED: events whose tile left the window since they were listed are
+        // dropped (mt only decreases), no candidate is touched.  Data with very many near-ties can keep the list full; then
+        // the thread evaluates what it has.
+        auto make_room = [&]() {
+            const float thr = mt + eps2;
+            int keep = 0;
+            for (int e = 0; e < cnt; ++e) {
+                const uint4 mb = evm[(size_t)e * kScanThreads];
+                const unsigned te = evt[(size_t)e * kScanThreads];
+                const float tmin = fminf(fminf(__uint_as_float(mb.x), __uint_as_float(mb.y)), fminf(__uint_as_float(mb.z), __uint_as_float(mb.w)));
+                if (!(tmin > thr)) {
+                    evm[(size_t)keep * kScanThreads] = mb;
+                    evt[(size_t)keep * kScanThreads] = te;
+                    ++keep;
+                }
+            }
+            cnt = keep;
+            if (cnt > kEvCap / 2) flush_own();
+        };
+        // After the sweep the warp works through the surviving (row, block) pairs of its 32 rows TOGETHER: lane c takes
+        // candidate c of the block, so a block is three coalesced 128-byte lines (per-thread evaluation makes every lane
+        // of every load touch its own line, and the L1 tag stage, one line per cycle, becomes the bound); the minimum
+        // and its lowest lane come from one REDUX + one ballot, and the row's owner lane keeps the result.  A row's pairs
+        // are consecutive and ascending, so strict '<' keeps the lowest index among exact ties.
+        auto flush_shared = [&]() {
+            const int keep = list_blocks();
+            CT_LAP(6);
+            int incl = keep;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += up;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            if (total > kEvCap * 32) {  // does not fit the pair list (warp-uniform)
+                for (int e = 0; e < keep; ++e) eval_block((int)blk_at(e) * 32, qx, qy, qz, best, bidx);
+            } else {
+                // every lane is past its events: the warp's evt slots become the pair list (block id << 5 | owner lane)
+                unsigned *list = &S.evt[0][warp * 32];
+                __syncwarp();
+                for (int e = 0; e < keep; ++e) {
+                    const int p = incl - keep + e;
+                    list[(size_t)(p >> 5) * kScanThreads + (p & 31)] = (blk_at(e) << 5) | (unsigned)lane;
+                }
+                __syncwarp();
+                const float kInfF = __int_as_float(0x7f800000);
+                constexpr int kBatch = 8;  // blocks whose loads are in flight together (one L2 round trip per batch)
+                for (int base = 0; base < total; base += kBatch) {
+                    unsigned pr[kBatch];
+                    float cx[kBatch], cy[kBatch], cz[kBatch];
+#pragma unroll
+                    for (int u = 0; u < kBatch; ++u) {
+                        const int p = min(base + u, total - 1);  // the tail repeats the last pair (harmless: strict '<')
+                        pr[u] = list[(size_t)(p >> 5) * kScanThreads + (p & 31)];
+                        const int j = min((int)(pr[u] >> 5) * 32 + lane, nc_loc - 1);
+                        const float *c = cb + (size_t)j * 3;
+                        cx[u] = __ldg(c), cy[u] = __ldg(c + 1), cz[u] = __ldg(c + 2);
                     }
-                } else {
-                    const int jend = min(j0 + 32, nc_loc);
-                    for (int j = j0; j < jend; ++j) cand(j, __ldg(cb + (size_t)j * 3), __ldg(cb + (size_t)j * 3 + 1), __ldg(cb + (size_t)j * 3 + 2));
+#pragma unroll
+                    for (int u = 0; u < kBatch; ++u) {
+                        const int r = (int)(pr[u] & 31u), j0 = (int)(pr[u] >> 5) * 32;
+                        const float x = __shfl_sync(0xffffffffu, qx, r), y = __shfl_sync(0xffffffffu, qy, r), z = __shfl_sync(0xffffffffu, qz, r);
+                        const float d = (j0 + lane < nc_loc) ? sqdist_ref(x, y, z, cx[u], cy[u], cz[u]) : kInfF;
+                        // d >= +0 (or +inf): the bit patterns order like the values
+                        const unsigned dm = __reduce_min_sync(0xffffffffu, __float_as_uint(d));
+                        const unsigned who = __ballot_sync(0xffffffffu, __float_as_uint(d) == dm);
+                        if (lane == r && __uint_as_float(dm) < best) {
+                            best = __uint_as_float(dm);
+                            bidx = j0 + (__ffs(who) - 1);
+                        }
+                    }
                 }
             }
             cnt = 0;
@@ -343,7 +426,6 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 bot
         const unsigned tbase = tmem + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(g * 2 * kHalfCols);
         const unsigned bfree0 = smem_u32(&S.b_free[0]);
         const bool group_leader = (warp & 3) == 0 && lane == 0;
-        CT_DECL;
         for (int t = 0; t < ntiles; ++t) {
             float bm0, bm1, bm2, bm3;
             {
@@ -385,11 +467,11 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 bot
                 evt[(size_t)cnt * kScanThreads] = (unsigned)t;
                 ++cnt;
             }
-            if (cnt >= kEvCap) flush();
+            if (cnt >= kEvCap) make_room();
         }
         CT_LAP(5);
-        flush();
-        CT_LAP(6);
+        flush_shared();
+        CT_LAP(7);
         CT_DUMP;
         const size_t off = (size_t)bi * a.nq + qrow;
         bool write = valid;

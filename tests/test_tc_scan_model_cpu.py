@@ -3,8 +3,10 @@ checked against brute force.
 
 The model follows the kernel's control flow for one query row: 128-candidate tiles of four 32-candidate blocks, the
 running minimum mt of the APPROXIMATE distances, a tile is listed when its minimum is <= mt + 2 eps, the list holds
-kEvCap tiles and is flushed when full, a flush re-checks each listed block against the current mt + 2 eps and evaluates
-the survivors exactly in ascending index order with strict '<'.  The approximate distances are the exact ones plus an
+kEvCap tiles; a full list is first COMPACTED (tiles whose minimum left the window are dropped, nothing is evaluated)
+and only if more than half of it survives the thread evaluates what it has; after the sweep each listed block is
+re-checked against the final mt + 2 eps and the survivors are evaluated exactly, ascending index with strict '<'
+(the kernel does that last step with the whole warp per block; the winner is the lowest lane of the minimum).  The approximate distances are the exact ones plus an
 ADVERSARIAL error of magnitude <= eps (random, all +eps, all -eps, alternating), so the test exercises the claim that
 any |dt - d| <= eps keeps the result exact, including the lowest-index rule on exact ties and list overflows."""
 import zlib
@@ -35,13 +37,20 @@ def scan_row(d_exact, dt, eps):
                     best, bidx = d_exact[j], j
         events = []
 
+    def make_room():
+        nonlocal events
+        thr = mt + 2 * eps
+        events = [(t, bms) for t, bms in events if not (bms.min() > thr)]
+        if len(events) > K_EV_CAP // 2:
+            flush()
+
     for t in range(len(dtp) // 128):
         bms = dtp[t * 128:(t + 1) * 128].reshape(4, 32).min(1)
         mt = min(mt, bms.min())
         if not (bms.min() > mt + 2 * eps):
             events.append((t, bms))
         if len(events) >= K_EV_CAP:
-            flush()
+            make_room()
     flush()
     return best, bidx, evaluated
 

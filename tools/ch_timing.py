@@ -36,7 +36,7 @@ if hasattr(L, "geom_debug_read_ch_timing"):
     t = buf.reshape(256, 20, 8).astype(np.float64) / 79.0   # cycles per tile (C2: 79 tiles)
     nsw = int(sys.argv[2]) if len(sys.argv) > 2 else 16   # scanner warps per CTA
     sc, pr = t[:, :nsw], t[:, nsw:nsw + nsw // 4]
-    names_s = ["wait full0", "ld0", "min0", "wait full1", "ld1", "min1+tail", "final flush"]
+    names_s = ["wait full0", "ld0", "min0", "wait full1", "ld1", "min1+tail", "flush: list", "flush: evaluate"]
     names_p = ["refill", "wait b_full", "wait e0", "mma0", "wait e1", "mma1"]
     print("  scanner cycles/tile :", "  ".join(f"{nm} {sc[:, :, i].mean():.0f}" for i, nm in enumerate(names_s)), f"  sum {sc[:, :, :6].sum(2).mean():.0f}")
     print("  producer cycles/tile:", "  ".join(f"{nm} {pr[:, :, i].mean():.0f}" for i, nm in enumerate(names_p)), f"  sum {pr[:, :, :6].sum(2).mean():.0f}")
