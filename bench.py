@@ -425,7 +425,7 @@ def run_product(args):
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         traffic, traffic_src = None, None
         try:  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[dom_name]
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))[dom_name]
             traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
         except Exception:
             pass
