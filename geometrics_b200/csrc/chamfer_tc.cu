@@ -161,9 +161,8 @@ struct ScanSmem {
 };
 
 // blockIdx.x -> (direction, batch item, row block, candidate chunk, chunks of this row block); see SearchArgs2
-__device__ __forceinline__ void decode_cta(const SearchArgs2 &both, int &dirsel, int &bi, int &rblock, int &chunk, int &nchunks)
+__device__ __forceinline__ void decode_cta(const SearchArgs2 &both, int rb_lin, int &dirsel, int &bi, int &rblock, int &chunk, int &nchunks)
 {
-    int rb_lin = (int)blockIdx.x;
     chunk = 0, nchunks = 1;
     if (rb_lin >= both.n_whole) {
         const int j = rb_lin - both.n_whole;
@@ -177,13 +176,42 @@ __device__ __forceinline__ void decode_cta(const SearchArgs2 &both, int &dirsel,
     bi = rb_dir / per_item, rblock = rb_dir % per_item;
 }
 
+// Everything a scanner thread needs about its row OUTSIDE the sweep (exact re-evaluation, result write-back), recomputed
+// from opaque copies of the block / thread index whenever it is needed: kept in registers through the sweep it would push the
+// loop over the 96-register budget of a 20-warp CTA and ptxas would rematerialise loop invariants every tile instead.
+struct RowCtx {
+    int dirsel, bi, rblock, chunk, nchunks;
+    int qrow;
+    bool valid, vec_ok;
+    float qx, qy, qz;
+    const float *cb;       // exact candidates of this CTA's first tile
+    int nc_loc, nc_full_loc, tile0;
+};
+__device__ __forceinline__ RowCtx row_ctx(const SearchArgs2 &both)
+{
+    int bx = (int)blockIdx.x, tx = (int)threadIdx.x;
+    asm volatile("" : "+r"(bx), "+r"(tx));  // opaque: no common subexpressions with the values computed before the sweep
+    RowCtx c;
+    decode_cta(both, bx, c.dirsel, c.bi, c.rblock, c.chunk, c.nchunks);
+    const SearchArgs &a = both.dir[c.dirsel];
+    c.qrow = c.rblock * kRowsPerCta + tx;  // scanner thread tx owns row tx of the CTA's 512
+    c.valid = c.qrow < a.nq;
+    const float *q = a.qxyz + ((size_t)c.bi * a.nq + min(c.qrow, a.nq - 1)) * 3;
+    c.qx = q[0], c.qy = q[1], c.qz = q[2];
+    c.tile0 = (int)((long long)((a.nc + kTileCols - 1) / kTileCols) * c.chunk / c.nchunks);
+    c.cb = a.cxyz + ((size_t)c.bi * a.nc_full + (size_t)c.tile0 * kTileCols) * 3;
+    c.nc_loc = a.nc - c.tile0 * kTileCols, c.nc_full_loc = a.nc_full - c.tile0 * kTileCols;
+    c.vec_ok = (((uintptr_t)c.cb) & 15u) == 0;
+    return c;
+}
+
 __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 both)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     ScanSmem &S = *reinterpret_cast<ScanSmem *>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     int dirsel, bi, rblock, chunk, nchunks;
-    decode_cta(both, dirsel, bi, rblock, chunk, nchunks);
+    decode_cta(both, (int)blockIdx.x, dirsel, bi, rblock, chunk, nchunks);
     const SearchArgs &a = both.dir[dirsel];
     const int row0 = rblock * kRowsPerCta;
     // this CTA sweeps candidate tiles [tile0, tile0 + ntiles) of the direction's tiles
@@ -265,17 +293,9 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 bot
         CT_DUMP;
     } else {
         // ================================ scanners ================================
-        const int g = warp >> 2;                  // row block == warp group
-        const int rloc = (warp & 3) * 32 + lane;  // row inside the block == TMEM lane
-        const int qrow = row0 + g * 128 + rloc;
-        const bool valid = qrow < a.nq;
-        float qx, qy, qz;
-        {
-            const float *q = a.qxyz + ((size_t)bi * a.nq + min(qrow, a.nq - 1)) * 3;
-            qx = q[0], qy = q[1], qz = q[2];
-        }
+        const int g = warp >> 2;                  // row block == warp group; TMEM lane == tid & 127
         // padding rows (zero operand: every dt is 0) start at -inf so that nothing ever passes their filter
-        float mt = valid ? __int_as_float(0x7f800000) : __int_as_float(0xff800000);
+        float mt = (row0 + tid < a.nq) ? __int_as_float(0x7f800000) : __int_as_float(0xff800000);
         float best = __int_as_float(0x7f800000);
         int bidx = 0;
         int cnt = 0;
@@ -285,9 +305,6 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 bot
         // while 12 R^2 << 1e30, hence the 1e13 bound)
         const float eps2 = (rmax < 1.0e13f) ? 2.0f * both.eps_scale * rmax * rmax : __int_as_float(0x7f800000);
         // candidate indices are local to this CTA's tile range inside the sweep (tile0 is added back at the end)
-        const float *cb = a.cxyz + ((size_t)bi * a.nc_full + (size_t)tile0 * kTileCols) * 3;
-        const int nc_loc = a.nc - tile0 * kTileCols, nc_full_loc = a.nc_full - tile0 * kTileCols;
-        const bool vec_ok = (((uintptr_t)cb) & 15u) == 0;
         uint4 *evm = &S.evm[0][tid];
         unsigned *evt = &S.evt[0][tid];
 
@@ -318,7 +335,9 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 bot
         };
         // Step 2 for one block: the reference's arithmetic on its 32 candidates, ascending index + strict '<' (lowest index
         // among exact ties), for the query (x, y, z).
-        auto eval_block = [&](int j0, float x, float y, float z, float &bd, int &bj) {
+        auto eval_block = [&](const RowCtx &c, int j0, float x, float y, float z, float &bd, int &bj) {
+            const float *cb = c.cb;
+            const int nc_loc = c.nc_loc;
             auto cand = [&](int j, float cx, float cy, float cz) {
                 const float d = sqdist_ref(x, y, z, cx, cy, cz);
                 if (j < nc_loc && d < bd) {
@@ -326,7 +345,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 bot
                     bj = j;
                 }
             };
-            if (vec_ok && j0 + 32 <= nc_full_loc) {
+            if (c.vec_ok && j0 + 32 <= c.nc_full_loc) {
                 const float4 *p = reinterpret_cast<const float4 *>(cb + (size_t)j0 * 3);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -344,7 +363,8 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 bot
         // Every thread evaluates its own blocks: max-over-lanes(blocks) rounds per warp.  Only the fallback.
         auto flush_own = [&]() {
             const int keep = list_blocks();
-            for (int e = 0; e < keep; ++e) eval_block((int)blk_at(e) * 32, qx, qy, qz, best, bidx);
+            const RowCtx c = row_ctx(both);
+            for (int e = 0; e < keep; ++e) eval_block(c, (int)blk_at(e) * 32, c.qx, c.qy, c.qz, best, bidx);
             cnt = 0;
         };
         // Inside the sweep a full list is only COMPACTED: events whose tile left the window since they were listed are
@@ -381,8 +401,12 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 bot
                 if (lane >= o) incl += up;
             }
             const int total = __shfl_sync(0xffffffffu, incl, 31);
+            const RowCtx c = row_ctx(both);
+            const float qx = c.qx, qy = c.qy, qz = c.qz;
+            const float *cb = c.cb;
+            const int nc_loc = c.nc_loc;
             if (total > kEvCap * 32) {  // does not fit the pair list (warp-uniform)
-                for (int e = 0; e < keep; ++e) eval_block((int)blk_at(e) * 32, qx, qy, qz, best, bidx);
+                for (int e = 0; e < keep; ++e) eval_block(c, (int)blk_at(e) * 32, qx, qy, qz, best, bidx);
             } else {
                 // every lane is past its events: the warp's evt slots become the pair list (block id << 5 | owner lane)
                 unsigned *list = &S.evt[0][warp * 32];
@@ -402,8 +426,8 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 bot
                         const int p = min(base + u, total - 1);  // the tail repeats the last pair (harmless: strict '<')
                         pr[u] = list[(size_t)(p >> 5) * kScanThreads + (p & 31)];
                         const int j = min((int)(pr[u] >> 5) * 32 + lane, nc_loc - 1);
-                        const float *c = cb + (size_t)j * 3;
-                        cx[u] = __ldg(c), cy[u] = __ldg(c + 1), cz[u] = __ldg(c + 2);
+                        const float *cp = cb + (size_t)j * 3;
+                        cx[u] = __ldg(cp), cy[u] = __ldg(cp + 1), cz[u] = __ldg(cp + 2);
                     }
 #pragma unroll
                     for (int u = 0; u < kBatch; ++u) {
@@ -459,9 +483,8 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 bot
                 bm2 = tree_min32(v, 0);
                 bm3 = tree_min32(v, 32);
             }
-            const float m4 = min3(min3(bm0, bm1, bm2), bm3, mt);
-            mt = m4;
-            const float tm = fminf(fminf(bm0, bm1), fminf(bm2, bm3));
+            const float tm = fminf(min3(bm0, bm1, bm2), bm3);
+            mt = fminf(mt, tm);
             if (!(tm > mt + eps2)) {  // predicated append: the tile holds a candidate inside the window
                 evm[(size_t)cnt * kScanThreads] = make_uint4(__float_as_uint(bm0), __float_as_uint(bm1), __float_as_uint(bm2), __float_as_uint(bm3));
                 evt[(size_t)cnt * kScanThreads] = (unsigned)t;
@@ -473,17 +496,19 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 bot
         flush_shared();
         CT_LAP(7);
         CT_DUMP;
-        const size_t off = (size_t)bi * a.nq + qrow;
+        const RowCtx c = row_ctx(both);  // nothing of the grid decode stayed live through the sweep
+        const SearchArgs &a = both.dir[c.dirsel];
+        const int bi = c.bi, rblock = c.rblock, chunk = c.chunk, nchunks = c.nchunks;
+        const bool valid = c.valid;
+        const size_t off = (size_t)bi * a.nq + c.qrow;
         bool write = valid;
-        int dirsel_, bi_, rblock, chunk, nchunks;  // recomputed: nothing of the grid decode stays live through the sweep
-        decode_cta(both, dirsel_, bi_, rblock, chunk, nchunks);
-        bidx += (int)((long long)((a.nc + kTileCols - 1) / kTileCols) * chunk / nchunks) * kTileCols;
+        bidx += c.tile0 * kTileCols;
         if (!(rmax < __int_as_float(0x7f800000))) {
             // Some input coordinate is NaN / Inf: the reference's answer depends on WHERE it sits in the 512-tiles
             // (chamfer_distance.cu:39,47), so every row is redone by the transcription of the reference loop.
             write = false;
             if (valid && chunk == 0) {
-                chamfer_ref_row(qx, qy, qz, a.cxyz + (size_t)bi * a.nc_full * 3, a.nc_full, both.exact != 0, best, bidx);
+                chamfer_ref_row(c.qx, c.qy, c.qz, a.cxyz + (size_t)bi * a.nc_full * 3, a.nc_full, both.exact != 0, best, bidx);
                 if (a.dist) a.dist[off] = best;
                 a.idx[off] = bidx;
             }
