@@ -286,6 +286,12 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 bot
                         "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n\t}" ::"r"(tmem_u + (unsigned)((g * 2 + h) * kHalfCols)),
                         "l"(da), "l"(db), "r"(idesc), "r"(0u), "r"(smem_u32(&S.full_bar[g][h]))
                         : "memory");
+                    // both MMAs of this row block on the tile are issued: their completion also releases the ring stage
+                    if (h == 1)
+                        asm volatile(
+                            "{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
+                            "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(&S.b_free[s]))
+                            : "memory");
                 }
                 CT_LAP(3 + 2 * h);
             }
@@ -447,9 +453,8 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 bot
             cnt = 0;
         };
 
-        const unsigned tbase = tmem + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(g * 2 * kHalfCols);
-        const unsigned bfree0 = smem_u32(&S.b_free[0]);
-        const bool group_leader = (warp & 3) == 0 && lane == 0;
+        // warp-uniform, visibly to ptxas (stays in a uniform register: no R2UR in front of every TMEM load)
+        const unsigned tbase = __shfl_sync(0xffffffffu, tmem + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(g * 2 * kHalfCols), 0);
         for (int t = 0; t < ntiles; ++t) {
             float bm0, bm1, bm2, bm3;
             {
@@ -472,8 +477,6 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 bot
                 mbar_wait(&S.full_bar[g][1], (unsigned)(t & 1));
                 CT_LAP(3);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                // both MMAs of this group on tile t are complete: the group no longer reads the ring stage
-                if (group_leader) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bfree0 + 8u * (unsigned)(t % kStages)) : "memory");
                 unsigned v[64];
                 tmem_ld64_wait(v, tbase + (unsigned)kHalfCols);
                 CT_LAP(4);
