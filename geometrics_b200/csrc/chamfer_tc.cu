@@ -443,10 +443,10 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 bot
                         // d >= +0 (or +inf): the bit patterns order like the values
                         const unsigned dm = __reduce_min_sync(0xffffffffu, __float_as_uint(d));
                         const unsigned who = __ballot_sync(0xffffffffu, __float_as_uint(d) == dm);
-                        if (lane == r && __uint_as_float(dm) < best) {
-                            best = __uint_as_float(dm);
-                            bidx = j0 + (__ffs(who) - 1);
-                        }
+                        // branch-free owner update: the eight blocks of a batch stay one straight-line instruction stream
+                        const bool upd = (lane == r) & (__uint_as_float(dm) < best);
+                        best = upd ? __uint_as_float(dm) : best;
+                        bidx = upd ? j0 + (__ffs(who) - 1) : bidx;
                     }
                 }
             }
@@ -459,7 +459,8 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 bot
             float bm0, bm1, bm2, bm3;
             {
                 CT_LAP(5);
-                mbar_wait(&S.full_bar[g][0], (unsigned)(t & 1));
+                // ONE wait per tile: the MMAs complete in order, so half 1 done implies half 0 done
+                mbar_wait(&S.full_bar[g][1], (unsigned)(t & 1));
                 CT_LAP(0);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 unsigned v[64];
@@ -474,7 +475,6 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 bot
             }
             {
                 CT_LAP(2);
-                mbar_wait(&S.full_bar[g][1], (unsigned)(t & 1));
                 CT_LAP(3);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 unsigned v[64];
