@@ -403,14 +403,14 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const ScanArgs a)
         const int rloc = (warp & 3) * 32 + lane;
         const int qrow = row0 + g * 128 + rloc;
         const bool valid = qrow < a.n;
-        V3 p;
+        V3 p0;
         {
             const float *q = a.xyz + ((size_t)bi * a.n + min(qrow, a.n - 1)) * 3;
-            p = v3(q[0], q[1], q[2]);
+            p0 = v3(q[0], q[1], q[2]);
         }
         const float R = __uint_as_float(*a.rmax_bits);
         const unsigned *rtile = a.ritem_bits + (size_t)bi * a.ntiles128;  // largest sphere radius per 128-triangle tile
-        const float pmax = fabsf(p.x) + fabsf(p.y) + fabsf(p.z);  // NaN / inf propagate
+        const float pmax = fabsf(p0.x) + fabsf(p0.y) + fabsf(p0.z);  // NaN / inf propagate
         // the filter needs finite operands of a magnitude the bf16 split handles; anything else: the reference loop below
         const bool filter_ok = (R < 1.0e15f) && (R > 1.0e-15f) && (pmax < kInf);  // false on NaN
         const bool active = valid && filter_ok;
@@ -424,7 +424,9 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const ScanArgs a)
         // minimum is "smaller distance wins, equal distances go to the lower face index" = the reference's rule
         // (distances are >= +0, so their bits order like their values; NaN never enters).
         S.key[tid] = ~0ull;
-        S.px[tid] = p.x, S.py[tid] = p.y, S.pz[tid] = p.z;
+        S.px[tid] = p0.x, S.py[tid] = p0.y, S.pz[tid] = p0.z;
+        // outside the sweeps the point is re-read from shared memory: three registers less through the TMEM loops
+        auto P = [&]() { return v3(S.px[tid], S.py[tid], S.pz[tid]); };
 #ifdef TRI_TC_TIMING
         unsigned long long tt_[16] = {};
 #endif
@@ -441,7 +443,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const ScanArgs a)
                 dead_now = false;
                 if (ti & (1u << 16)) {
                     float opt;
-                    const float d0 = pair_exact_compact(p, recb + (size_t)t * 128 * kRecVec4, opt);
+                    const float d0 = pair_exact_compact(P(), recb + (size_t)t * 128 * kRecVec4, opt);
                     dead_now = d0 != d0;
                     if (t == 0) poisoned = dead_now;
                 }
@@ -457,7 +459,8 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const ScanArgs a)
         const unsigned tbase = tmem + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(g * 2 * kHalfCols);
         // one half tile: wait for its MMA, pull the 64 values, hand the accumulator back
         auto pull = [&](unsigned (&v)[64], int tt, int h) {
-            mbar_wait(&S.full_bar[g][h], (unsigned)(tt & 1));
+            // ONE wait per tile: the MMAs complete in order, so half 1 done implies half 0 done
+            if (h == 0) mbar_wait(&S.full_bar[g][1], (unsigned)(tt & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             tmem_ld64_wait(v, tbase + (unsigned)(h * kHalfCols));
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -498,6 +501,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const ScanArgs a)
         ref_pos = 0;
         // the triangle of that group with the smallest fp32 sphere value gives the first exact distance U0
         if (active && bg >= 0) {
+            const V3 p = P();
             float4 s8[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) s8[i] = __ldg(sphb + bg * 8 + i);
@@ -510,7 +514,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const ScanArgs a)
                 if (s8[i].w >= 0.0f && s8[i].w < kInf && hh < hb) hb = hh, jb = bg * 8 + i;
             }
             if (jb >= 0) {
-                const float d = tri_pair_fast(p, load_compact(recb + (size_t)jb * kRecVec4));
+                const float d = tri_pair_fast(P(), load_compact(recb + (size_t)jb * kRecVec4));
                 if (d == d) S.key[tid] = make_key(d, (unsigned)jb);
             }
         }
@@ -679,7 +683,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const ScanArgs a)
                     float tb = 10000.0f;
                     int tb_i = 0;
                     for (int k = 0; k < end_ka; ++k) {
-                        const float dk = tri_pair_fast(p, load_compact(recb + (size_t)(k2 + k) * kRecVec4));
+                        const float dk = tri_pair_fast(P(), load_compact(recb + (size_t)(k2 + k) * kRecVec4));
                         if (k == 0 || dk < tb) {
                             tb = dk;
                             tb_i = k2 + k;
@@ -693,15 +697,15 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const ScanArgs a)
                 }
                 if (!res_empty) {
                     idx = res_i;
-                    d = pair_exact_compact(p, recb + (size_t)idx * kRecVec4, opt);
+                    d = pair_exact_compact(P(), recb + (size_t)idx * kRecVec4, opt);
                 }
             } else {
                 if (poisoned) {
                     idx = 0;
-                    d = pair_exact_compact(p, recb, opt);
+                    d = pair_exact_compact(P(), recb, opt);
                 } else if (S.key[tid] != ~0ull) {
                     idx = (int)(unsigned)S.key[tid];
-                    d = pair_exact_compact(p, recb + (size_t)idx * kRecVec4, opt);
+                    d = pair_exact_compact(P(), recb + (size_t)idx * kRecVec4, opt);
                 }
                 if (a.empty_tail && d > 10000.0f) {
                     d = 10000.0f;
