@@ -626,10 +626,11 @@ size_t workspace_bytes(int b, int n, int m)
 
 // Grid plan: row blocks that fill whole waves of the one-CTA-per-SM grid sweep all their candidate tiles; the remaining
 // row blocks are split `chunks` ways so that the last wave covers the GPU too.  Costs in tile-steps, fitted on B200
-// (profiles/r02_tc_chunks.txt): a CTA costs its tiles + ~16 tiles of prologue, pipeline fill, final flush and key merge.
+// (profiles/r02_tc_chunks.txt, table 3): a CTA costs its tiles + ~26 tile-steps of prologue, pipeline fill, final
+// re-evaluation and key merge (the absolute overhead, ~11 us, has not changed since the first fit; the tile-step got faster).
 static void plan_grid(long long row_blocks, int tiles, int sms, int &n_whole, int &chunks)
 {
-    const double kCtaOverhead = 16.0;
+    const double kCtaOverhead = 26.0;
     const long long rem = row_blocks % sms;
     n_whole = (int)row_blocks;
     chunks = 1;
