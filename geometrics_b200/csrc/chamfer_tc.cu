@@ -116,7 +116,19 @@ __device__ unsigned long long g_ch_timing[256 * 20 * 8];
 #define CT_DECL unsigned long long ct_[8] = {}; unsigned long long ct_t_ = clock64()
 #define CT_LAP(slot) do { const unsigned long long n_ = clock64(); ct_[slot] += n_ - ct_t_; ct_t_ = n_; } while (0)
 #define CT_DUMP do { if (lane == 0 && blockIdx.x < 256) for (int i_ = 0; i_ < 8; ++i_) g_ch_timing[((size_t)blockIdx.x * 20 + warp) * 8 + i_] = ct_[i_]; } while (0)
+// absolute time line of the CTA (thread 0): globaltimer stamps + SM id
+__device__ unsigned long long g_ch_stamps[2048 * 8];
+__device__ __forceinline__ unsigned long long gtime()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define CT_STAMP(i) do { if (threadIdx.x == 0 && blockIdx.x < 2048) g_ch_stamps[(size_t)blockIdx.x * 8 + (i)] = gtime(); } while (0)
+#define CT_SMID do { if (threadIdx.x == 0 && blockIdx.x < 2048) { unsigned sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); g_ch_stamps[(size_t)blockIdx.x * 8 + 7] = sm_; } } while (0)
 #else
+#define CT_STAMP(i) do { } while (0)
+#define CT_SMID do { } while (0)
 #define CT_DECL do { } while (0)
 #define CT_LAP(slot) do { } while (0)
 #define CT_DUMP do { } while (0)
@@ -209,6 +221,8 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 bot
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     ScanSmem &S = *reinterpret_cast<ScanSmem *>(smem_raw);
+    CT_STAMP(0);
+    CT_SMID;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     int dirsel, bi, rblock, chunk, nchunks;
     decode_cta(both, (int)blockIdx.x, dirsel, bi, rblock, chunk, nchunks);
@@ -246,6 +260,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 bot
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const unsigned tmem = S.tmem_slot;
+    CT_STAMP(1);
 
     if (warp >= kGroups * 4) {
         // ================================ producers (one warp per row block) ================================
@@ -461,6 +476,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 bot
                 CT_LAP(5);
                 // ONE wait per tile: the MMAs complete in order, so half 1 done implies half 0 done
                 mbar_wait(&S.full_bar[g][1], (unsigned)(t & 1));
+                if (t == 0) CT_STAMP(2);
                 CT_LAP(0);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 unsigned v[64];
@@ -496,8 +512,10 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 bot
             if (cnt >= kEvCap) make_room();
         }
         CT_LAP(5);
+        CT_STAMP(3);
         flush_shared();
         CT_LAP(7);
+        CT_STAMP(4);
         CT_DUMP;
         const RowCtx c = row_ctx(both);  // nothing of the grid decode stayed live through the sweep
         const SearchArgs &a = both.dir[c.dirsel];
@@ -540,9 +558,11 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const SearchArgs2 bot
             a.idx[off] = bidx;
         }
     }
+    CT_STAMP(5);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((unsigned)kTmemCols));
+    CT_STAMP(6);
 }
 
 // Test hook (geom_debug_tc_dump): the approximate squared distances exactly as the tensor core delivers them -- one CTA,
@@ -609,6 +629,10 @@ __global__ void __launch_bounds__(128) dump_kernel(const uint4 *__restrict__ for
 extern "C" __attribute__((visibility("default"))) int geom_debug_read_ch_timing(unsigned long long *host, size_t count)
 {
     return (int)cudaMemcpyFromSymbol(host, geom::chamfer_tc::g_ch_timing, count * sizeof(unsigned long long));
+}
+extern "C" __attribute__((visibility("default"))) int geom_debug_read_ch_stamps(unsigned long long *host, size_t count)
+{
+    return (int)cudaMemcpyFromSymbol(host, geom::chamfer_tc::g_ch_stamps, count * sizeof(unsigned long long));
 }
 #endif
 namespace geom {

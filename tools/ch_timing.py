@@ -41,3 +41,18 @@ if hasattr(L, "geom_debug_read_ch_timing"):
     print("  scanner cycles/tile :", "  ".join(f"{nm} {sc[:, :, i].mean():.0f}" for i, nm in enumerate(names_s)), f"  sum {sc[:, :, :6].sum(2).mean():.0f}")
     print("  producer cycles/tile:", "  ".join(f"{nm} {pr[:, :, i].mean():.0f}" for i, nm in enumerate(names_p)), f"  sum {pr[:, :, :6].sum(2).mean():.0f}")
     print("  producer g=0        :", "  ".join(f"{nm} {pr[:, 0, i].mean():.0f}" for i, nm in enumerate(names_p)))
+    if hasattr(L, "geom_debug_read_ch_stamps"):
+        L.geom_debug_read_ch_stamps.argtypes = [C.c_void_p, C.c_size_t]
+        sb = np.zeros(2048 * 8, np.uint64)
+        assert L.geom_debug_read_ch_stamps(sb.ctypes.data, sb.size) == 0
+        st = sb.reshape(2048, 8)[:1280].astype(np.int64)
+        names = ["entry -> barriers/TMEM ready", "-> first tile ready", "-> sweep done", "-> re-evaluation done", "-> results written", "-> TMEM freed (exit)"]
+        d = np.diff(st[:, :7], axis=1) / 1000.0
+        print("  CTA time line (us, mean / median over 1280 CTAs):", "  ".join(f"{n} {d[:, i].mean():.2f}/{np.median(d[:, i]):.2f}" for i, n in enumerate(names)), f"  total {(st[:, 6] - st[:, 0]).mean() / 1000.0:.2f}")
+        # gap between consecutive CTAs on the same SM
+        gaps = []
+        for sm in np.unique(st[:, 7]):
+            rows = st[st[:, 7] == sm]
+            rows = rows[np.argsort(rows[:, 0])]
+            gaps += list((rows[1:, 0] - rows[:-1, 6]) / 1000.0)
+        print(f"  gap between a CTA's exit and the next CTA's entry on the same SM: mean {np.mean(gaps):.2f} us, median {np.median(gaps):.2f} us;  kernel span {(st[:, 6].max() - st[:, 0].min()) / 1000.0:.1f} us")
