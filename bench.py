@@ -171,20 +171,26 @@ class ClockSampler:
             self._h = None
         self._t = threading.Thread(target=self._loop, daemon=True)
 
-    def _loop(self):
+    def sample(self):
+        """One reading (SM clock + throttle reasons) from the calling thread."""
+        if self._h is None:
+            return
         nv = self._nv
-        while not self._stop.is_set():
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
             try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
-                try:
-                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
-                except Exception:
-                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
-                for bit, name in self.REASONS.items():
-                    if mask & bit:
-                        self.reasons.add(name)
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
             except Exception:
-                pass
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+            for bit, name in self.REASONS.items():
+                if mask & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def _loop(self):
+        while not self._stop.is_set():
+            self.sample()
             self._stop.wait(0.005)
 
     def start(self):
@@ -340,8 +346,15 @@ def run_product(args):
     drain()
     barrier()
     _note("warm-up done")
+    # Clocks of the timed region: read from THIS thread once every step is enqueued and the GPU is still working through
+    # them (and every 5 ms after that until the region ends).  A sampling thread started beside the enqueue loop makes its
+    # first NVML calls while the host is launching; with 8 ranks on one box that stalled the launches of a 2-ms region
+    # for several ms (r02: 0.29 ms/step timed against 0.09 sustained).
     sampler = ClockSampler(_physical_gpu_index(local))
-    sampler.start()
+    sampler.sample()      # NVML paths warm before the region; this reading is dropped
+    sampler.samples.clear()
+    sampler.reasons.clear()
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     h0 = time.perf_counter()
@@ -350,6 +363,10 @@ def run_product(args):
     host_us = (time.perf_counter() - h0) / args.steps * 1e6  # host time to enqueue one step
     drain()
     e1.record(stream)
+    sampler.sample()      # everything is enqueued, the device is inside the region
+    while not e1.query():
+        sampler.sample()
+        time.sleep(0.005)
     barrier()
     ms_total = e0.elapsed_time(e1)
     clocks = sampler.stop()
