@@ -14,22 +14,23 @@
 //      k-chunk major), so a block is ONE contiguous 4 KB TMA bulk copy.
 //   2. scan_kernel: a CTA owns 4 x 128 query rows and streams 128-candidate tiles through a TMA ring.
 //      Row block g has two TMEM accumulators (64 candidates each), a producer warp that issues
-//      tcgen05.mma (M128 N64 K16) into whichever of the two is free, and four scanner warps (one per TMEM
-//      lane quarter) that pull 64 columns with tcgen05.ld, hand the accumulator back and reduce the
-//      values with 3-input minima (0.5 instruction per pair).  A thread owns one query row for the whole
-//      sweep.  No exact arithmetic inside the sweep: with mt = running minimum of dt for the row, a
-//      32-candidate block whose minimum bm satisfies bm <= mt + 2 eps is appended to the thread's EVENT
-//      list in shared memory (predicated store, no branch).  After the sweep (or when the list is nearly
-//      full) the thread re-evaluates, with the reference's exact fp32 sequence (sqdist_ref), every
-//      candidate of the listed blocks that still satisfy bm <= mt + 2 eps, in ascending index order
-//      with strict '<'.
+//      tcgen05.mma (M128 N64 K16) into whichever of the two is free (one elected lane, warp-uniform operands), and
+//      four scanner warps (one per TMEM lane quarter) that pull 64 columns with tcgen05.ld, hand the accumulator
+//      back and reduce the values with 3-input minima (0.5 instruction per pair).  A thread owns one query row
+//      for the whole sweep.  No exact arithmetic inside the sweep: with mt = running minimum of dt for the row,
+//      a tile that holds a 32-candidate block with minimum bm <= mt + 2 eps is appended to the thread's EVENT
+//      list in shared memory (predicated store, no branch); a full list is compacted (tiles that left the
+//      window are dropped).  After the sweep the warp re-evaluates, with the reference's exact fp32 sequence
+//      (sqdist_ref), every candidate of the listed blocks that still satisfy bm <= mt + 2 eps: lane c takes
+//      candidate c of a block, the minimum and its lowest lane come from REDUX + ballot, the row's owner lane
+//      keeps the result with strict '<' (blocks of a row in ascending order).
 //      Correctness: the true nearest neighbour j* has dt(j*) <= d(j*) + eps <= d(jt) + eps <=
 //      dt(jt) + 2 eps = mt_final + 2 eps (jt = argmin dt); mt only decreases, so the block of j* is
 //      listed when it is scanned and survives every later re-check.  Candidates with the same exact
 //      distance as j* satisfy the same bound, so the lowest index among exact ties is found too
 //      (chamfer_distance.cu:39,47).
 //
-// One launch covers both directions (blockIdx.z); ~0.9 instructions per pair instead of ~10.
+// One launch covers both directions (1-D grid, see SearchArgs2); ~1 instruction per pair instead of ~10.
 #include "tc_common.cuh"
 
 namespace geom {
