@@ -13,9 +13,9 @@
 //     for anything, split it into hi/lo TF32 and store both in the canonical no-swizzle K-major layout
 //     ([16-byte k-chunk][row][16 B]) as soon as the MMAs that last read that buffer have completed;
 //   * the W tile comes pre-split and pre-arranged in that layout (wsplit_kernel, once per call: W is
-//     small); one thread fetches its eight 4 KB planes with TMA bulk copies (mbarrier complete_tx);
-//   * the same thread issues 2 k-substeps x 3 tcgen05.mma (kind::tf32, K = 8) and commits to the buffer's
-//     mbarrier.
+//     small); warp 0 fetches its eight 4 KB planes with TMA bulk copies (mbarrier complete_tx);
+//   * warp 0 (one elected lane, warp-uniform operands) issues 2 k-substeps x 3 tcgen05.mma (kind::tf32, K = 8) and
+//     commits to the buffer's mbarrier.
 // Epilogue: tcgen05.ld -> shared-memory transpose -> coalesced row writes with the 0N-GCN routing
 // (columns < ksplit to the smoothing scratch T, the rest straight to Y with bias / ReLU).
 #include "common.cuh"
@@ -56,12 +56,21 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
 
+// Called by a whole (converged) warp with warp-uniform operands: ONE elected lane issues.  Under `if (tid == 0)` ptxas wraps
+// every tcgen05 / bulk-copy instruction in a per-lane R2UR.BROADCAST loop (~240 cycles per MMA + commit).
 __device__ __forceinline__ void mma_tf32(unsigned tmem_d, u64 da, u64 db, unsigned idesc, unsigned accumulate)
 {
     asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "{\n\t.reg .pred p, pe;\n\telect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
         "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit(unsigned long long *bar)
+{
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar))
         : "memory");
 }
 
@@ -107,11 +116,14 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
     }
 }
 // TMA bulk copy global -> shared, completion counted in bytes on `bar` (expect_tx posted by the caller)
+// (whole warp, one elected lane copies)
 __device__ __forceinline__ void tma_load(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *bar)
 {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
-                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
+        "@pe cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}" ::"r"(smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
 }
 
 __global__ void __launch_bounds__(kThreads, 2) gemm_kernel(const Args g)
@@ -133,10 +145,13 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_kernel(const Args g)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(ncols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    auto load_b = [&](int s) {  // one thread: eight plane copies of stage s into buffer s & 1
+    auto load_b = [&](int s) {  // warp 0, one elected lane: eight plane copies of stage s into buffer s & 1
         unsigned char *sb = buf_of(s) + abytes;
         const unsigned plane = (unsigned)g.Npad * 16u;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&b_full[s & 1])), "r"(2u * kChunks * plane) : "memory");
+        asm volatile(
+            "{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
+            "@pe mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(smem_u32(&b_full[s & 1])), "r"(2u * kChunks * plane)
+            : "memory");
         const uint4 *ghi = g.Bhi + (size_t)s * kChunks * g.Npad;
         const uint4 *glo = g.Blo + (size_t)s * kChunks * g.Npad;
 #pragma unroll
@@ -152,6 +167,9 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_kernel(const Args g)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 0) {
+        __syncwarp();  // the barriers are initialised (by lane 0, which is also the lane elect.sync picks)
         load_b(0);
     }
     // D = f32 (1<<4), A = B = tf32 (2<<7, 2<<10), both K-major, N>>3 at bit 17, M>>4 at bit 24
@@ -207,7 +225,8 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_kernel(const Args g)
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (tid == 0) {
+        if (warp == 0) {
+            const unsigned tmem_u = __shfl_sync(0xffffffffu, tmem, 0);  // warp-uniform, visibly to ptxas
             mbar_wait(&b_full[s & 1], (unsigned)((s >> 1) & 1));
 #pragma unroll
             for (int sub = 0; sub < BK / 8; ++sub) {  // one K = 8 MMA covers chunks 2*sub, 2*sub+1
@@ -216,11 +235,11 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_kernel(const Args g)
                 const u64 bh = make_desc(smem_u32(sBhi + 2 * sub * bplane), bplane, 128);
                 const u64 bl = make_desc(smem_u32(sBlo + 2 * sub * bplane), bplane, 128);
                 const unsigned first = (s == 0 && sub == 0) ? 0u : 1u;
-                mma_tf32(tmem, al, bh, idesc, first);  // small terms first
-                mma_tf32(tmem, ah, bl, idesc, 1u);
-                mma_tf32(tmem, ah, bh, idesc, 1u);
+                mma_tf32(tmem_u, al, bh, idesc, first);  // small terms first
+                mma_tf32(tmem_u, ah, bl, idesc, 1u);
+                mma_tf32(tmem_u, ah, bh, idesc, 1u);
             }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mma_done[s & 1])) : "memory");
+            mma_commit(&mma_done[s & 1]);
             if (s + 1 < g.nstages) {
                 // the other buffer's W planes are read by the MMAs of stage s-1: refill it once they are done
                 if (s >= 1) mbar_wait(&mma_done[(s + 1) & 1], (unsigned)(((s - 1) >> 1) & 1));
